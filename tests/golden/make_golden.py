@@ -1,0 +1,349 @@
+"""Generate the golden fixtures under tests/golden/ by RUNNING THE REFERENCE.
+
+Run once, in the build container (``/root/reference`` is not present on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference (``/root/reference/src/qrisp``) imports jax, qiskit and matplotlib at module
+scope; none of them is installed here and none of them is on the simulator path, so
+``_refstub`` satisfies those imports with inert stubs (``jax.numpy`` is mapped to numpy,
+which is all ``QuantumFloat.decoder`` needs).  Everything recorded below is computed by the
+reference's own ``qrisp.simulator`` code: ``Operation.get_unitary``, ``statevector_sim``,
+``run`` and ``group_qc``.
+
+Fixtures written (all small .npz files):
+
+* gates.npz        -- unitary of every standard gate the B200 gate library offers
+* statevector.npz  -- circuits + ``statevector_sim`` output
+* run.npz          -- circuits with (mid-circuit) measurements + ``run(qc, None)`` output
+* programs.npz     -- circuits Qrisp itself compiled (BASELINE.json configs[0]: QuantumFloat
+                      h + inverse QFT; configs[2]: Shor ``find_order``) + what ``run`` returned
+* fusion.npz       -- ``group_qc`` output: every grouped instruction's qubits and unitary
+"""
+
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import _refstub  # noqa: E402
+
+_refstub.install()
+_refstub.patch()
+
+import qrisp  # noqa: E402
+from qrisp import QFT, PGate, QuantumCircuit, QuantumFloat, RZGate, h  # noqa: E402
+from qrisp.simulator import run, statevector_sim  # noqa: E402
+from qrisp.simulator.circuit_preprocessing import group_qc  # noqa: E402
+
+from qrisp_b200.circuit import Circuit  # noqa: E402
+
+
+def quiet(f, *a, **k):
+    """The reference prints a tqdm bar; keep the log readable."""
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f(*a, **k)
+
+
+def pack(prefix, circuit, out):
+    for k, v in circuit.to_arrays().items():
+        out[prefix + k] = v
+
+
+# ------------------------------------------------------------------------------------
+def make_gates():
+    out = {}
+    specs = [
+        ("h", lambda qc: qc.h(0), 1),
+        ("x", lambda qc: qc.x(0), 1),
+        ("y", lambda qc: qc.y(0), 1),
+        ("z", lambda qc: qc.z(0), 1),
+        ("s", lambda qc: qc.s(0), 1),
+        ("s_dg", lambda qc: qc.s_dg(0), 1),
+        ("t", lambda qc: qc.t(0), 1),
+        ("t_dg", lambda qc: qc.t_dg(0), 1),
+        ("sx", lambda qc: qc.sx(0), 1),
+        ("p", lambda qc: qc.p(0.37, 0), 1),
+        ("rx", lambda qc: qc.rx(0.37, 0), 1),
+        ("ry", lambda qc: qc.ry(0.37, 0), 1),
+        ("rz", lambda qc: qc.rz(0.37, 0), 1),
+        ("u3", lambda qc: qc.u3(0.37, 1.1, -0.6, 0), 1),
+        ("gphase", lambda qc: qc.gphase(0.37, 0), 1),
+        ("cx", lambda qc: qc.cx(0, 1), 2),
+        ("cy", lambda qc: qc.cy(0, 1), 2),
+        ("cz", lambda qc: qc.cz(0, 1), 2),
+        ("cp", lambda qc: qc.cp(0.37, 0, 1), 2),
+        ("crz", lambda qc: qc.append(RZGate(0.37).control(1), [qc.qubits[0], qc.qubits[1]]), 2),
+        ("swap", lambda qc: qc.swap(0, 1), 2),
+        ("rzz", lambda qc: qc.rzz(0.37, 0, 1), 2),
+        ("rxx", lambda qc: qc.rxx(0.37, 0, 1), 2),
+        ("mcx", lambda qc: qc.mcx([0, 1], 2), 3),
+        ("mcp", lambda qc: qc.append(PGate(0.37).control(2), [qc.qubits[0], qc.qubits[1], qc.qubits[2]]), 3),
+    ]
+    names = []
+    for name, build, n in specs:
+        qc = QuantumCircuit(n)
+        build(qc)
+        # per-instruction unitary (what the simulator multiplies with) ...
+        out["op_" + name] = np.asarray(qc.data[0].op.get_unitary(), dtype=np.complex128)
+        out["opq_" + name] = np.array([qc.qubits.index(q) for q in qc.data[0].qubits])
+        names.append(name)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "gates.npz"), **out)
+    print("gates.npz:", len(names), "gates")
+
+
+# ------------------------------------------------------------------------------------
+def random_qrisp_circuit(n, depth, rng, measure=False):
+    qc = QuantumCircuit(n)
+    one = ["h", "x", "y", "z", "s", "t", "sx", "p", "rx", "ry", "rz", "u3"]
+    two = ["cx", "cy", "cz", "cp", "crz", "swap", "rzz", "rxx"]
+    for _ in range(depth):
+        r = rng.random()
+        if r < 0.45 or n == 1:
+            g = one[rng.integers(len(one))]
+            q = int(rng.integers(n))
+            if g in ("p", "rx", "ry", "rz"):
+                getattr(qc, g)(float(rng.uniform(-3, 3)), q)
+            elif g == "u3":
+                qc.u3(*(float(x) for x in rng.uniform(-3, 3, 3)), q)
+            else:
+                getattr(qc, g)(q)
+        elif r < 0.9 or n == 2:
+            g = two[rng.integers(len(two))]
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            if g == "crz":
+                qc.append(RZGate(float(rng.uniform(-3, 3))).control(1), [qc.qubits[a], qc.qubits[b]])
+            elif g in ("cp", "rzz", "rxx"):
+                getattr(qc, g)(float(rng.uniform(-3, 3)), a, b)
+            else:
+                getattr(qc, g)(a, b)
+        else:
+            a, b, c = (int(x) for x in rng.choice(n, 3, replace=False))
+            if rng.random() < 0.5:
+                qc.mcx([a, b], c)
+            else:
+                qc.append(PGate(float(rng.uniform(-3, 3))).control(2), [qc.qubits[a], qc.qubits[b], qc.qubits[c]])
+    return qc
+
+
+def ghz_qft_qrisp(n):
+    qc = QuantumCircuit(n)
+    qc.h(0)
+    for i in range(n - 1):
+        qc.cx(i, i + 1)
+    for j in range(n):
+        qc.h(j)
+        for k in range(j + 1, n):
+            qc.cp(math.pi / (1 << (k - j)), k, j)
+    for j in range(n // 2):
+        qc.swap(j, n - 1 - j)
+    return qc
+
+
+def make_statevector():
+    rng = np.random.default_rng(1234)
+    out = {}
+    cases = []
+    for n, depth in [(1, 6), (2, 12), (3, 20), (4, 30), (5, 40), (6, 60), (7, 60), (8, 80), (10, 120), (12, 150)]:
+        cases.append((f"rand{n}", random_qrisp_circuit(n, depth, rng)))
+    for n in (3, 6, 11):
+        cases.append((f"ghzqft{n}", ghz_qft_qrisp(n)))
+    names = []
+    for name, qc in cases:
+        sv = quiet(statevector_sim, qc.copy())
+        pack(name + "_", Circuit.from_qrisp(qc), out)
+        out[name + "_sv"] = np.asarray(sv, dtype=np.complex64)
+        names.append(name)
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "statevector.npz"), **out)
+    print("statevector.npz:", names)
+
+
+# ------------------------------------------------------------------------------------
+def make_run():
+    rng = np.random.default_rng(4321)
+    out = {}
+    cases = []
+
+    # all qubits measured at the end
+    for n, depth in [(2, 8), (3, 20), (5, 40), (8, 60)]:
+        qc = random_qrisp_circuit(n, depth, rng)
+        qc.measure(qc.qubits)
+        cases.append((f"full{n}", qc))
+
+    # a subset measured, clbits in scrambled order
+    qc = random_qrisp_circuit(6, 50, rng)
+    for q in (4, 1, 3):
+        qc.measure(qc.qubits[q])
+    cases.append(("subset6", qc))
+
+    # more than 10 measured qubits -> the reference's cutoff-ratio branch
+    qc = random_qrisp_circuit(12, 100, rng)
+    qc.measure(qc.qubits)
+    cases.append(("full12", qc))
+
+    # mid-circuit measurement followed by further gates on the same qubit
+    qc = QuantumCircuit(3)
+    qc.h(0)
+    qc.cx(0, 1)
+    qc.measure(qc.qubits[0])
+    qc.h(0)
+    qc.cx(0, 2)
+    qc.measure(qc.qubits[0])
+    qc.measure(qc.qubits[2])
+    cases.append(("midcircuit", qc))
+
+    # measurement, reset, reuse
+    qc = QuantumCircuit(2)
+    qc.h(0)
+    qc.cx(0, 1)
+    qc.measure(qc.qubits[0])
+    qc.reset(qc.qubits[0])
+    qc.ry(0.7, 0)
+    qc.measure(qc.qubits[0])
+    qc.measure(qc.qubits[1])
+    cases.append(("reset_reuse", qc))
+
+    # reset without measurement
+    qc = QuantumCircuit(2)
+    qc.h(0)
+    qc.cx(0, 1)
+    qc.reset(qc.qubits[0])
+    qc.rx(1.1, 0)
+    qc.measure(qc.qubits)
+    cases.append(("reset_only", qc))
+
+    # GHZ + QFT, all measured
+    qc = ghz_qft_qrisp(9)
+    qc.measure(qc.qubits)
+    cases.append(("ghzqft9", qc))
+
+    names = []
+    for name, qc in cases:
+        res = quiet(run, qc.copy(), None)
+        pack(name + "_", Circuit.from_qrisp(qc), out)
+        keys = sorted(res.keys())
+        out[name + "_keys"] = np.array(keys)
+        out[name + "_probs"] = np.array([res[k] for k in keys], dtype=np.float64)
+        names.append(name)
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "run.npz"), **out)
+    print("run.npz:", names)
+
+
+# ------------------------------------------------------------------------------------
+def make_programs():
+    """Circuits compiled by Qrisp itself, captured at the backend boundary."""
+    import qrisp.interface.simulators.qrisp_simulator_backend as be
+
+    captured = []
+    orig = be.default_run
+
+    def spy(qc, shots, token=""):
+        res = orig(qc.copy(), shots, token)
+        captured.append((qc.copy(), shots, res))
+        return res
+
+    be.default_run = spy
+    out = {}
+    names = []
+
+    def record(name):
+        qc, shots, res = captured[-1]
+        pack(name + "_", Circuit.from_qrisp(qc), out)
+        keys = sorted(res.keys())
+        out[name + "_keys"] = np.array(keys)
+        out[name + "_probs"] = np.array([res[k] for k in keys], dtype=np.float64)
+        names.append(name)
+
+    # BASELINE.json configs[0]: 20-qubit QuantumFloat, h, inverse QFT, get_measurement
+    for size in (6, 20):
+        qf = QuantumFloat(size)
+        h(qf)
+        QFT(qf, inv=True)
+        mes = quiet(lambda: dict(qf.get_measurement()))
+        record(f"qfloat_h_iqft{size}")
+        out[f"qfloat_h_iqft{size}_decoded_keys"] = np.array([float(k) for k in mes.keys()])
+        out[f"qfloat_h_iqft{size}_decoded_probs"] = np.array([float(v) for v in mes.values()])
+
+    # a small arithmetic program: exercises qb_alloc / qb_dealloc and uncomputation
+    a = QuantumFloat(3)
+    b = QuantumFloat(3)
+    a[:] = 3
+    h(b[0])
+    h(b[1])
+    c = a * b
+    quiet(lambda: dict(c.get_measurement()))
+    record("qfloat_mul3")
+
+    # BASELINE.json configs[2]: Shor order finding via QuantumModulus (README example)
+    from qrisp import QuantumModulus, control
+
+    def find_order_mes(a_, N):
+        qg = QuantumModulus(N)
+        qg[:] = 1
+        qpe_res = QuantumFloat(2 * qg.size + 1, exponent=-(2 * qg.size + 1))
+        h(qpe_res)
+        x = a_
+        for i in range(len(qpe_res)):
+            with control(qpe_res[i]):
+                qg *= x
+                x = (x * x) % N
+        QFT(qpe_res, inv=True)
+        return dict(qpe_res.get_measurement())
+
+    for a_, N in ((2, 7), (4, 15)):
+        try:
+            quiet(find_order_mes, a_, N)
+            record(f"shor_order_a{a_}_N{N}")
+        except Exception as e:  # pragma: no cover - depends on the stubbed imports
+            print("shor", a_, N, "failed under stubs:", repr(e)[:200])
+
+    be.default_run = orig
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "programs.npz"), **out)
+    print("programs.npz:", names)
+
+
+# ------------------------------------------------------------------------------------
+def make_fusion():
+    rng = np.random.default_rng(99)
+    out = {}
+    names = []
+    for n, depth in [(4, 30), (6, 60), (9, 100)]:
+        qc = random_qrisp_circuit(n, depth, rng)
+        name = f"group{n}"
+        pack(name + "_", Circuit.from_qrisp(qc), out)
+        gqc = quiet(group_qc, qc.copy())
+        # each grouped instruction: its qubits (circuit indices) and the unitary the
+        # reference's main loop would apply (simulator.py:145 -> op.get_unitary())
+        goff, gq, gm = [0], [], []
+        for instr in gqc.data:
+            gq.extend(gqc.qubits.index(q) for q in instr.qubits)
+            goff.append(len(gq))
+            gm.append(np.asarray(instr.op.get_unitary(), dtype=np.complex128).ravel())
+        out[name + "_goff"] = np.array(goff)
+        out[name + "_gq"] = np.array(gq)
+        out[name + "_gm"] = np.concatenate(gm)
+        out[name + "_sv"] = np.asarray(quiet(statevector_sim, qc.copy()), dtype=np.complex64)
+        names.append(name)
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "fusion.npz"), **out)
+    print("fusion.npz:", names)
+
+
+if __name__ == "__main__":
+    make_gates()
+    make_statevector()
+    make_run()
+    make_programs()
+    make_fusion()
