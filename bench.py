@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of the B200 statevector path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the CPU reference arm
+
+Workload (BASELINE.json configs[1]): GHZ preparation + QFT on 30 qubits, complex64, one
+B200; with N > 1 GPUs the register grows by log2(N) qubits (weak scaling: 2**30 amplitudes
+per GPU), the state is sharded by its high positions and global qubits are swapped in with
+an NCCL all-to-all.  A "step" simulates the whole circuit on a fresh |0...0> state.
+
+One JSON line on stdout (rank 0).  `value` is device-timed with the compiled passes already
+resident in HBM; `e2e` goes through the public API with host inputs (circuit object in,
+sampled counts dict out) and includes planning, the H2D copy of the pass descriptors, the
+sweep, device-side sampling and the D2H copy of the samples.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+METRIC = "statevector_gates_per_s"
+UNIT = "gates/s"
+LOCAL_QUBITS = 30
+CPU_SAMPLE_QUBITS = 22
+E2E_SHOTS = 4096
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (recipe: B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(smax)) if smax else None,
+            "power_w_max": float(max(power)) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle (port of the reference's algorithm) on the host cores
+# ----------------------------------------------------------------------------------------
+
+
+def cpu_gates_per_s(sample_qubits, budget_s=25.0):
+    """Times oracle.ref_sim.apply_matrix over the GHZ+QFT circuit at `sample_qubits` and
+    scales to the 30-qubit workload by amplitude count (the reference's cost per gate is
+    linear in the state size: tensor_factor.py:67-89 reshapes and multiplies the whole
+    state once per gate)."""
+    from oracle import ref_sim
+    from qrisp_b200.circuit import ghz_qft_circuit
+
+    qc = ghz_qft_circuit(sample_qubits)
+    instrs = [i for i in qc.data if i.matrix is not None]
+    psi = ref_sim.zero_state(sample_qubits)
+    t0 = time.perf_counter()
+    done = 0
+    for instr in instrs:
+        psi = ref_sim.apply_matrix(psi, instr.matrix, instr.qubits, sample_qubits, threshold=False)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    n_total = LOCAL_QUBITS + int(np.log2(args.gpus))
+    vals = []
+    for _ in range(max(1, args.warmup)):
+        cpu_gates_per_s(CPU_SAMPLE_QUBITS, budget_s=2.0)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        g, done, dt = cpu_gates_per_s(CPU_SAMPLE_QUBITS, budget_s=max(5.0, 120.0 / args.steps))
+        vals.append(g)
+    wall = time.perf_counter() - t_all
+    scale = 2.0 ** (CPU_SAMPLE_QUBITS - n_total)
+    value = float(np.mean(vals)) * scale
+    sample = (f"oracle/ref_sim.py (numpy port of the reference's per-gate contraction) on GHZ+QFT at "
+              f"{CPU_SAMPLE_QUBITS} qubits, gates/s scaled by 2**({CPU_SAMPLE_QUBITS}-{n_total}) to the "
+              f"{n_total}-qubit workload (cost per gate is linear in the state size)")
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "complex64",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    n_total = LOCAL_QUBITS + int(np.log2(n_gpus))
+    return {
+        "workload": f"GHZ + QFT on {n_total} qubits, dense statevector, complex64 (BASELINE.json configs[1]"
+        + ("" if n_gpus == 1 else f", widened by log2({n_gpus}) qubits for weak scaling") + ")",
+        "qubits": n_total,
+        "local_qubits": LOCAL_QUBITS,
+        "state_bytes_per_gpu": 8 << LOCAL_QUBITS,
+        "l2": "state (8 GiB per GPU) is 65x the 126 MB L2: no flush needed between steps",
+        "parallelism": "single GPU" if n_gpus == 1 else f"state sharded by the top {int(np.log2(n_gpus))} positions",
+    }
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+
+
+def run_gpu_arm(args):
+    import torch
+
+    from qrisp_b200 import _lib
+    from qrisp_b200.circuit import ghz_qft_circuit
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    lib = _lib.load()
+    n_total = LOCAL_QUBITS + int(np.log2(world))
+    qc = ghz_qft_circuit(n_total)
+    instrs = [i for i in qc.data if i.matrix is not None]
+    n_gates = len(instrs)
+
+    if world == 1:
+        from qrisp_b200.engine import StateVector
+
+        sv = StateVector(n_total)
+    else:
+        from qrisp_b200.distributed import ShardedStateVector
+
+        sv = ShardedStateVector(n_total, group=dist.group.WORLD)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- compile once: the timed region replays the resident program
+    canonical_pos = list(sv.pos)
+    prog = sv.compile(instrs)
+    final_pos = list(sv.pos)
+
+    def step():
+        sv.reset()
+        sv.pos[:] = canonical_pos
+        prog.run()
+        sv.pos[:] = final_pos
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.qb2_reset_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    pass_ms = []
+    barrier()
+    ev_start, ev_end = ev[-2], ev[-1]
+    ev_start.record()
+    marks = []
+    for k in range(args.steps):
+        sv.reset()
+        sv.pos[:] = canonical_pos
+        ev[2 * k].record()
+        prog.run()
+        ev[2 * k + 1].record()
+        sv.pos[:] = final_pos
+    ev_end.record()
+    barrier()
+    launches = int(lib.qb2_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev_start.elapsed_time(ev_end)
+    sweep_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps))
+    t = torch.tensor([total_ms, sweep_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, sweep_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = n_gates / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (pass_kernel): algorithmic bytes = read + write of
+    # the local state once per launch
+    n_pass = prog.n_passes
+    state_bytes = 8 << LOCAL_QUBITS
+    comm_ms = getattr(prog, "comm_ms", None)
+    pass_avg_ms = sweep_ms / args.steps / max(1, n_pass) if world == 1 else None
+    peak, peak_src = measured_peaks()
+    if world > 1:
+        pass_avg_ms = prog.measure_pass_ms()
+    achieved = 2 * state_bytes / (pass_avg_ms * 1e-3) / 1e9
+    roofline = {
+        "kernel": "pass_kernel<float,4,256,4>",
+        "bound": "hbm",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": 2 * state_bytes,
+        "avg_launch_ms": pass_avg_ms,
+        "passes_per_step": n_pass,
+        "kernel_ops_per_step": prog.n_kernel_ops,
+        "phases_per_step": prog.n_phases,
+    }
+    traffic_path = os.path.join(ROOT, "profiles", "pass_kernel_traffic.json")
+    if os.path.exists(traffic_path):
+        try:
+            roofline["traffic"] = json.load(open(traffic_path)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the public API: circuit object in, counts dict out
+    from qrisp_b200.circuit import Circuit
+
+    e2e = None
+    if world == 1:
+        from qrisp_b200.simulator import sample_counts
+
+        qc_m = Circuit(n_total)
+        qc_m.data = list(qc.data)
+        qc_m.measure(list(range(n_total)))
+        del sv, prog
+        torch.cuda.empty_cache()
+        sample_counts(qc_m, 16, seed=0)  # warm-up
+        torch.cuda.synchronize()
+        reps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for i in range(reps):
+            counts = sample_counts(qc_m, E2E_SHOTS, seed=i)
+            assert sum(counts.values()) == E2E_SHOTS
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / reps
+        from qrisp_b200 import simulator as _s
+
+        e2e = {
+            "value": n_gates / e2e_s,
+            "unit": UNIT,
+            "ms_per_step": 1e3 * e2e_s,
+            "h2d_bytes_per_step": int(_s.LAST_H2D_BYTES),
+            "d2h_bytes_per_step": int(_s.LAST_D2H_BYTES),
+            "api": f"qrisp_b200.simulator.sample_counts(circuit, shots={E2E_SHOTS}): plan + upload + sweep + device sampling",
+        }
+    else:
+        e2e = sv.e2e_report(qc, E2E_SHOTS, n_gates) if hasattr(sv, "e2e_report") else None
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        g, done, dt = cpu_gates_per_s(CPU_SAMPLE_QUBITS, budget_s=20.0)
+        scale = 2.0 ** (CPU_SAMPLE_QUBITS - n_total)
+        cpu_baseline = {
+            "value": g * scale,
+            "unit": UNIT,
+            "cores": cpu_threads(),
+            "kind": "port",
+            "sample": f"oracle/ref_sim.py on the first {done} gates of GHZ+QFT at {CPU_SAMPLE_QUBITS} qubits "
+            f"({dt:.1f} s), gates/s scaled by 2**({CPU_SAMPLE_QUBITS}-{n_total}) to the {n_total}-qubit workload",
+        }
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": UNIT,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "complex64",
+        "data": "synthetic",
+        "config": workload_config(world),
+        "gates_per_step": n_gates,
+        "amp_updates_per_s": value * float(1 << n_total),
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "e2e": e2e,
+    }
+    if comm_ms is not None:
+        line["comm_ms_per_step"] = comm_ms
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.gpus < 1 or args.gpus & (args.gpus - 1):
+        raise SystemExit("--gpus must be a power of two")
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+A numpy interpreter of the packed pass format of ``include/qrisp_b200.h`` (qb2_pass_header,
+qb2_phase, qb2_op, qb2_tab).  It executes a blob the way ``pass_kernel`` in
+``qrisp_b200/csrc/qb2_pass.cu`` does -- same thread/register distribution, same
+shared-memory slot maps, same table lookups -- so that the host planner
+(``qrisp_b200/planner.py``) can be checked on a machine without a GPU, and so that the GPU
+tests have a second, independent reading of the format.  Nothing under ``qrisp_b200/``
+imports this module.
+
+It also reports the bank-conflict degree of every exchange so that the planner's claim
+("both sides conflict free") is tested, not assumed.
+"""
+
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+MAGIC = 0x32425151
+
+
+class ParsedPass:
+    pass
+
+
+def parse(blob):
+    b = bytes(blob)
+    (magic, total, small, n, T, r, dtype, n_seg, n_phases, phases_off, ops_off, coef_off, u16_off, u64_off,
+     tabdesc_off, tab_off, n_ops, _, _) = struct.unpack_from("<IIIIBBBBIIIIIIIII2I", b, 0)
+    assert magic == MAGIC and total == len(b), (hex(magic), total, len(b))
+    P = ParsedPass()
+    P.n, P.T, P.r, P.dtype, P.small = n, T, r, dtype, small
+    P.segs = [struct.unpack_from("<BBBB", b, 64 + 4 * i)[:3] for i in range(n_seg)]
+    P.phases = [struct.unpack_from("<8I", b, phases_off + 32 * i)[:6] for i in range(n_phases)]
+    P.ops = []
+    for i in range(n_ops):
+        cmask, cval, jmask, data, kind, b0, b1, nthr, nreg = struct.unpack_from("<QQIIBBBBB", b, ops_off + 32 * i)
+        P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, kind=kind, b0=b0, b1=b1, nthr=nthr, nreg=nreg))
+    real_t = np.float32 if dtype == 0 else np.float64
+    frac_t = np.uint32 if dtype == 0 else np.uint64
+    P.real_t, P.frac_t = real_t, frac_t
+    P.coefs = np.frombuffer(b, dtype=real_t, count=(u64_off - coef_off) // np.dtype(real_t).itemsize, offset=coef_off)
+    P.a64 = np.frombuffer(b, dtype=np.uint64, count=(tabdesc_off - u64_off) // 8, offset=u64_off)
+    ntd = (u16_off - tabdesc_off) // 32
+    P.tabs = []
+    for i in range(ntd):
+        raw = struct.unpack_from("<24BII", b, tabdesc_off + 32 * i)
+        pieces = [(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2]) for k in range(6)]
+        P.tabs.append(dict(pieces=pieces, off=raw[24], regoff=raw[25]))
+    P.a16 = np.frombuffer(b, dtype=np.uint16, count=(small - u16_off) // 2, offset=u16_off)
+    P.tables = np.frombuffer(b, dtype=frac_t, count=(total - tab_off) // np.dtype(frac_t).itemsize, offset=tab_off)
+    return P
+
+
+def _tab_index(tab, X):
+    idx = np.zeros(X.shape, dtype=np.uint64)
+    for shift, ln, out in tab["pieces"]:
+        if ln:
+            idx |= ((X >> np.uint64(shift)) & np.uint64((1 << ln) - 1)) << np.uint64(out)
+    return idx
+
+
+def _phase(turns, dtype):
+    """exp(2 pi i turns / 2**bits) in the pass precision (the kernel's own approximation is
+    good to ~1e-7; the emulator uses the exact value)."""
+    if dtype == 0:
+        ang = turns.astype(np.float64) * (2 * np.pi / 4294967296.0)
+    else:
+        ang = turns.astype(np.int64).astype(np.float64) * (2 * np.pi / 18446744073709551616.0)
+    return np.exp(1j * ang)
+
+
+def run(blob, state, hi_base=0, report=None):
+    """Apply the pass to ``state`` (complex numpy array of 2**n, modified copy returned)."""
+    P = parse(blob)
+    n, T, r = P.n, P.T, P.r
+    NR, TB = 1 << r, T - r
+    nthreads = 1 << TB
+    cdt = np.complex64 if P.dtype == 0 else np.complex128
+    state = np.array(state, dtype=cdt)
+    assert state.size == 1 << n
+    tid = np.arange(nthreads, dtype=np.uint64)
+    ntiles = 1 << (n - T)
+    conflict_lanes = 16 if P.dtype == 0 else 8
+
+    def thread_cols(base_idx, arr, xor):
+        acc = np.zeros(nthreads, dtype=np.uint64)
+        for b in range(TB):
+            v = np.uint64(int(arr[base_idx + b]))
+            sel = ((tid >> np.uint64(b)) & np.uint64(1)).astype(bool)
+            acc[sel] = (acc[sel] ^ v) if xor else (acc[sel] | v)
+        return acc
+
+    for t in range(ntiles):
+        tbase = 0
+        for src, dst, ln in P.segs:
+            tbase |= ((t >> src) & ((1 << ln) - 1)) << dst
+        ph0 = P.phases[0]
+        xloc = np.uint64(tbase) | thread_cols(ph0[2], P.a64, False)
+        rp = P.a64[ph0[3] : ph0[3] + NR]
+        addr = xloc[:, None] | rp[None, :]
+        regs = state[addr.astype(np.int64)]  # [thread, j]
+        seen = np.zeros(1 << T, dtype=bool)
+        for pi, (first_op, nops, pcol, rphys, xw, xr) in enumerate(P.phases):
+            if pi > 0:
+                tile = np.zeros(1 << T, dtype=cdt)
+                filled = np.zeros(1 << T, dtype=bool)
+                wb = thread_cols(xw, P.a16, True)
+                slots = (wb[:, None] ^ P.a16[xw + TB : xw + TB + NR].astype(np.uint64)[None, :]).astype(np.int64)
+                assert slots.max() < (1 << T)
+                assert not filled[slots.reshape(-1)].any() and len(np.unique(slots)) == slots.size, "store slots collide"
+                tile[slots] = regs
+                _check_conflicts(slots, conflict_lanes, report, "store", pi)
+                rb = thread_cols(xr, P.a16, True)
+                slots = (rb[:, None] ^ P.a16[xr + TB : xr + TB + NR].astype(np.uint64)[None, :]).astype(np.int64)
+                assert len(np.unique(slots)) == slots.size, "load slots collide"
+                regs = tile[slots]
+                _check_conflicts(slots, conflict_lanes, report, "load", pi)
+                xloc = np.uint64(tbase) | thread_cols(pcol, P.a64, False)
+            X = np.uint64(hi_base) | xloc
+            for o in range(first_op, first_op + nops):
+                op = P.ops[o]
+                if op["kind"] == 5:
+                    tb = P.tabs[op["data"] : op["data"] + op["nthr"] + op["nreg"]]
+                    s = np.zeros(nthreads, dtype=P.frac_t)
+                    for tdesc in tb[: op["nthr"]]:
+                        s = s + P.tables[(np.uint64(tdesc["off"]) + _tab_index(tdesc, X)).astype(np.int64)]
+                    sj = np.repeat(s[:, None], NR, axis=1)
+                    for tdesc in tb[op["nthr"] :]:
+                        base = np.uint64(tdesc["off"]) + _tab_index(tdesc, X)
+                        go = P.a16[tdesc["regoff"] : tdesc["regoff"] + NR].astype(np.uint64)
+                        sj = sj + P.tables[(base[:, None] + go[None, :]).astype(np.int64)]
+                    regs = (regs * _phase(sj, P.dtype)).astype(cdt)
+                else:
+                    k = op["kind"]
+                    D = 1 << k
+                    bits = [op["b0"], op["b1"]][:k] if k <= 2 else list(range(k))
+                    m = P.coefs[2 * op["data"] : 2 * op["data"] + 2 * D * D].astype(np.float64)
+                    m = (m[0::2] + 1j * m[1::2]).reshape(D, D)
+                    on = ((X ^ np.uint64(op["cval"])) & np.uint64(op["cmask"])) == 0
+                    tmask = sum(1 << bb for bb in bits)
+                    new = regs.copy()
+                    for base in range(NR):
+                        if base & tmask or not (op["jmask"] >> base) & 1:
+                            continue
+                        js = [base | sum(((c >> i) & 1) << bits[i] for i in range(k)) for c in range(D)]
+                        x = regs[:, js].astype(np.complex128)
+                        y = x @ m.T
+                        new[np.ix_(on, js)] = y[on].astype(cdt)
+                    regs = new
+        last = P.phases[-1]
+        rp = P.a64[last[3] : last[3] + NR]
+        addr = (xloc[:, None] | rp[None, :]).astype(np.int64)
+        state[addr] = regs
+    return state
+
+
+def _check_conflicts(slots, lanes, report, side, phase):
+    """Worst bank-conflict degree over wavefronts of ``lanes`` consecutive threads."""
+    if report is None:
+        return
+    nthreads = slots.shape[0]
+    lanes = min(lanes, nthreads)
+    worst = 1
+    for j in range(slots.shape[1]):
+        g = slots[:, j].reshape(-1, lanes) % lanes  # bank group of each lane
+        for row in g:
+            worst = max(worst, int(np.bincount(row, minlength=lanes).max()))
+    report.append((phase, side, worst))

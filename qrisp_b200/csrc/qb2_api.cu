@@ -1,0 +1,146 @@
+// qb2_api.cu -- the extern "C" boundary of libqb2.so (include/qrisp_b200.h).
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "qb2_internal.cuh"
+
+namespace qb2 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return QB2_OK;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+        return set_error(QB2_ENODEV, "%s: %s", what, cudaGetErrorString(e));
+    return set_error(QB2_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            cached = sms;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+static int check_dtype(int dtype, const char *who) {
+    if (dtype != QB2_C64 && dtype != QB2_C128) return set_error(QB2_EINVAL, "%s: bad dtype %d", who, dtype);
+    return QB2_OK;
+}
+
+}  // namespace qb2
+
+using namespace qb2;
+
+extern "C" {
+
+int qb2_abi_version(void) { return QB2_ABI_VERSION; }
+
+const char *qb2_last_error(void) { return g_err; }
+
+int qb2_device_info(int *sm_count_out, int *smem_optin_bytes, size_t *total_mem_bytes) {
+    int dev = 0;
+    QB2_CUDA(cudaGetDevice(&dev));
+    int sms = 0, smem = 0;
+    QB2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    QB2_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    size_t free_b = 0, total_b = 0;
+    QB2_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    if (sm_count_out) *sm_count_out = sms;
+    if (smem_optin_bytes) *smem_optin_bytes = smem;
+    if (total_mem_bytes) *total_mem_bytes = total_b;
+    return QB2_OK;
+}
+
+uint64_t qb2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void qb2_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
+
+int qb2_malloc(void **dev_ptr, size_t bytes) {
+    if (!dev_ptr) return set_error(QB2_EINVAL, "qb2_malloc: null pointer");
+    QB2_CUDA(cudaMalloc(dev_ptr, bytes));
+    return QB2_OK;
+}
+int qb2_free(void *dev_ptr) {
+    QB2_CUDA(cudaFree(dev_ptr));
+    return QB2_OK;
+}
+int qb2_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream) {
+    QB2_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return QB2_OK;
+}
+int qb2_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    QB2_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return QB2_OK;
+}
+int qb2_stream_sync(void *stream) {
+    QB2_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return QB2_OK;
+}
+
+int qb2_init_basis(void *state, int n, uint64_t basis, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_init_basis")) return rc;
+    return launch_init_basis(state, n, basis, dtype, (cudaStream_t)stream);
+}
+
+int qb2_run_pass(void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev, int dtype,
+                 void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_run_pass")) return rc;
+    return launch_pass(state, n, hi_base, reinterpret_cast<const qb2_pass_header *>(header), blob_dev, dtype,
+                       (cudaStream_t)stream);
+}
+
+int qb2_apply_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev,
+                         const int *targets, int k, uint64_t ctrl_mask, uint64_t ctrl_value, int dtype,
+                         void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_apply_matrix_big")) return rc;
+    return launch_matrix_big(src, dst, n, hi_base, matrix_dev, targets, k, ctrl_mask, ctrl_value, dtype,
+                             (cudaStream_t)stream);
+}
+
+int qb2_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_permute_bits")) return rc;
+    return launch_permute_bits(src, dst, n, perm, dtype, (cudaStream_t)stream);
+}
+
+int qb2_norm2(const void *state, int n, double *out_dev, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_norm2")) return rc;
+    return launch_norm2(state, n, out_dev, dtype, (cudaStream_t)stream);
+}
+
+int qb2_probabilities(const void *state, int n, uint64_t hi_base, const int *mes_pos, int m, double *probs_dev,
+                      int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_probabilities")) return rc;
+    return launch_probabilities(state, n, hi_base, mes_pos, m, probs_dev, dtype, (cudaStream_t)stream);
+}
+
+int qb2_sample_chunk_bits(int n) { return sample_chunk_bits(n); }
+
+int qb2_sample_prepare(const void *state, int n, double *chunk_sums_dev, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_sample_prepare")) return rc;
+    return launch_sample_prepare(state, n, chunk_sums_dev, dtype, (cudaStream_t)stream);
+}
+
+int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, const double *uniforms_dev,
+                    int64_t shots, uint64_t *indices_dev, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_sample_draw")) return rc;
+    return launch_sample_draw(state, n, chunk_sums_dev, uniforms_dev, shots, indices_dev, dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// Internal helpers shared by the translation units of libqb2.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "qrisp_b200.h"
+
+namespace qb2 {
+
+template <typename real>
+struct Traits;
+template <>
+struct Traits<float> {
+    using vec = float2;
+    using frac = uint32_t;
+    static constexpr int dtype = QB2_C64;
+};
+template <>
+struct Traits<double> {
+    using vec = double2;
+    using frac = uint64_t;
+    static constexpr int dtype = QB2_C128;
+};
+
+// error plumbing (qb2_api.cu)
+int set_error(int code, const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);
+void count_launch();
+int sm_count();
+
+#define QB2_CUDA(call)                                   \
+    do {                                                 \
+        int _rc = ::qb2::check_cuda((call), #call);      \
+        if (_rc != QB2_OK) return _rc;                   \
+    } while (0)
+
+// launchers implemented per translation unit
+int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, int dtype,
+                cudaStream_t s);
+int launch_init_basis(void *state, int n, uint64_t basis, int dtype, cudaStream_t s);
+int launch_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev, const int *targets,
+                      int k, uint64_t cmask, uint64_t cval, int dtype, cudaStream_t s);
+int launch_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, cudaStream_t s);
+int launch_norm2(const void *state, int n, double *out_dev, int dtype, cudaStream_t s);
+int launch_probabilities(const void *state, int n, uint64_t hi_base, const int *mes_pos, int m, double *probs_dev,
+                         int dtype, cudaStream_t s);
+int launch_sample_prepare(const void *state, int n, double *chunk_sums_dev, int dtype, cudaStream_t s);
+int launch_sample_draw(const void *state, int n, const double *chunk_sums_dev, const double *uniforms_dev,
+                       int64_t shots, uint64_t *indices_dev, int dtype, cudaStream_t s);
+int sample_chunk_bits(int n);
+
+}  // namespace qb2

@@ -1,0 +1,451 @@
+// qb2_measure.cu -- measurement, sampling, layout and the big-matrix correctness path.
+//
+//   norm2 / probabilities : BiArray.squared_norm, DenseBiArray.multi_measure
+//                           (reference: bi_arrays.py:1030-1059, bi_array_helper.py:315-387)
+//   sample_prepare / draw : numpy.random.choice over cl_prob (simulator.py:190-201)
+//   permute_bits          : TensorFactor.swap / unravel (tensor_factor.py:56-64, :163-169)
+//   matrix_big            : TensorFactor.apply_matrix for unitaries wider than a pass holds
+#include "qb2_internal.cuh"
+
+namespace qb2 {
+
+namespace {
+
+struct BitRuns {  // index transform: out |= ((in >> src) & mask(len)) << dst
+    int n;
+    uint8_t src[48], dst[48], len[48];
+};
+
+__device__ __forceinline__ uint64_t apply_runs(const BitRuns &r, const uint64_t in) {
+    uint64_t out = 0;
+    for (int i = 0; i < r.n; ++i) out |= ((in >> r.src[i]) & ((1ull << r.len[i]) - 1ull)) << r.dst[i];
+    return out;
+}
+
+template <typename vec>
+__device__ __forceinline__ double abs2(const vec v) {
+    return (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+}
+
+// ------------------------------------------------------------------ permute_bits
+template <typename vec>
+__global__ void permute_bits_kernel(const vec *__restrict__ src, vec *__restrict__ dst, const uint64_t size,
+                                    const BitRuns runs) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < size; j += stride)
+        dst[j] = src[apply_runs(runs, j)];
+}
+
+// ------------------------------------------------------------------ norm2
+__device__ __forceinline__ double block_sum(double v, double *sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    double t = (threadIdx.x < (unsigned)nw) ? sh[threadIdx.x] : 0.0;
+    if (w == 0)
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    __syncthreads();
+    return t;  // valid in warp 0
+}
+
+template <typename vec>
+__global__ void norm2_kernel(const vec *__restrict__ state, const uint64_t size, double *__restrict__ out) {
+    __shared__ double sh[32];
+    double acc = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += stride) acc += abs2(state[i]);
+    const double t = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
+// ------------------------------------------------------------------ probabilities
+struct MesDesc {
+    int m;
+    int8_t pos[64];  // pos[k]: physical position of outcome bit (m-1-k)
+};
+
+constexpr int PROB_CHUNK_BITS = 12;
+constexpr int PROB_THREADS = 256;
+
+template <typename vec>
+__global__ void __launch_bounds__(PROB_THREADS)
+    probabilities_kernel(const vec *__restrict__ state, const int n, const int C, const uint64_t hi_base,
+                         const MesDesc md, double *__restrict__ probs) {
+    extern __shared__ double vals[];
+    __shared__ int8_t lo_out[PROB_CHUNK_BITS];  // outcome bit of the measured local positions, ascending position
+    __shared__ int n_lo;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t csize = 1u << C;
+    const uint64_t nchunks = 1ull << (n - C);
+    if (tid == 0) {
+        int a = 0;
+        for (int p = 0; p < C; ++p)
+            for (int k = 0; k < md.m; ++k)
+                if (md.pos[k] == p) lo_out[a++] = (int8_t)(md.m - 1 - k);
+        n_lo = a;
+    }
+    __syncthreads();
+    const int a = n_lo;
+    for (uint64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const vec *src = state + (chunk << C);
+        for (uint32_t i = tid; i < csize; i += PROB_THREADS) vals[i] = abs2(__ldcs(src + i));
+        __syncthreads();
+        // fold away the non-measured local positions, highest first
+        uint32_t S = csize;
+        for (int p = C - 1; p >= 0; --p) {
+            bool measured = false;
+            for (int k = 0; k < md.m; ++k) measured |= (md.pos[k] == p);
+            if (measured) continue;
+            // current index of position p = number of positions below it (none of them folded yet)
+            const int q = p;
+            const uint32_t half = S >> 1;
+            double tmp[(1 << PROB_CHUNK_BITS) / 2 / PROB_THREADS];
+#pragma unroll
+            for (int it = 0; it < (1 << PROB_CHUNK_BITS) / 2 / PROB_THREADS; ++it) {
+                const uint32_t k = tid + it * PROB_THREADS;
+                if (k < half) {
+                    const uint32_t i0 = ((k >> q) << (q + 1)) | (k & ((1u << q) - 1u));
+                    tmp[it] = vals[i0] + vals[i0 | (1u << q)];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int it = 0; it < (1 << PROB_CHUNK_BITS) / 2 / PROB_THREADS; ++it) {
+                const uint32_t k = tid + it * PROB_THREADS;
+                if (k < half) vals[k] = tmp[it];
+            }
+            __syncthreads();
+            S = half;
+        }
+        // outcome bits fixed by the chunk number and the rank bits
+        const uint64_t X = hi_base | (chunk << C);
+        uint64_t o_hi = 0;
+        for (int k = 0; k < md.m; ++k)
+            if (md.pos[k] >= C) o_hi |= ((X >> md.pos[k]) & 1ull) << (md.m - 1 - k);
+        for (uint32_t k = tid; k < S; k += PROB_THREADS) {
+            uint64_t o = o_hi;
+            for (int b = 0; b < a; ++b) o |= (uint64_t)((k >> b) & 1u) << lo_out[b];
+            const double v = vals[k];
+            if (v != 0.0) atomicAdd(probs + o, v);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ sampling
+constexpr int SAMPLE_THREADS = 256;
+
+template <typename vec>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+    chunk_sums_kernel(const vec *__restrict__ state, const int cb, const uint64_t nchunks, double *__restrict__ sums) {
+    __shared__ double sh[32];
+    const uint32_t csize = 1u << cb;
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const vec *src = state + (c << cb);
+        double acc = 0;
+        for (uint32_t i = threadIdx.x; i < csize; i += SAMPLE_THREADS) acc += abs2(__ldcs(src + i));
+        const double t = block_sum(acc, sh);
+        if (threadIdx.x == 0) sums[c] = t;
+    }
+}
+
+// single CTA, in-place inclusive scan
+__global__ void __launch_bounds__(1024) scan_kernel(double *__restrict__ v, const uint64_t n) {
+    __shared__ double part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t per = (n + 1023) / 1024;
+    const uint64_t lo = tid * per, hi = (lo + per < n) ? lo + per : n;
+    double acc = 0;
+    for (uint64_t i = lo; i < hi; ++i) acc += v[i];
+    part[tid] = acc;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        const double add = (tid >= o) ? part[tid - o] : 0.0;
+        __syncthreads();
+        part[tid] += add;
+        __syncthreads();
+    }
+    double run = (tid > 0) ? part[tid - 1] : 0.0;
+    for (uint64_t i = lo; i < hi; ++i) {
+        run += v[i];
+        v[i] = run;
+    }
+}
+
+template <typename vec>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+    sample_draw_kernel(const vec *__restrict__ state, const int cb, const uint64_t nchunks,
+                       const double *__restrict__ cums, const double *__restrict__ uniforms, const int64_t shots,
+                       uint64_t *__restrict__ indices) {
+    __shared__ double incl[SAMPLE_THREADS];
+    __shared__ uint64_t s_chunk;
+    __shared__ double s_resid;
+    __shared__ int s_pick, s_last;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t csize = 1u << cb;
+    const uint32_t seg = csize >= SAMPLE_THREADS ? csize / SAMPLE_THREADS : 1;
+    const double total = cums[nchunks - 1];
+    for (int64_t shot = blockIdx.x; shot < shots; shot += gridDim.x) {
+        if (tid == 0) {
+            double target = uniforms[shot] * total;
+            const double below = nextafter(total, 0.0);
+            if (target > below) target = below;
+            if (target < 0) target = 0;
+            // first chunk whose inclusive sum exceeds the target
+            uint64_t lo = 0, hi = nchunks - 1;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (cums[mid] > target)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            s_chunk = lo;
+            s_resid = target - (lo > 0 ? cums[lo - 1] : 0.0);
+            s_pick = -1;
+            s_last = -1;
+        }
+        __syncthreads();
+        const uint64_t c = s_chunk;
+        const double resid = s_resid;
+        const vec *src = state + (c << cb);
+        const uint32_t start = tid * seg;
+        double mine = 0;
+        if (start < csize)
+            for (uint32_t i = 0; i < seg; ++i) mine += abs2(src[start + i]);
+        incl[tid] = mine;
+        __syncthreads();
+        for (uint32_t o = 1; o < SAMPLE_THREADS; o <<= 1) {
+            const double add = (tid >= o) ? incl[tid - o] : 0.0;
+            __syncthreads();
+            incl[tid] += add;
+            __syncthreads();
+        }
+        const double my_incl = incl[tid];
+        const double my_excl = my_incl - mine;
+        if (mine > 0.0) {
+            atomicMax(&s_last, (int)tid);
+            if (my_incl > resid && my_excl <= resid) atomicMax(&s_pick, (int)tid);
+        }
+        __syncthreads();
+        const int pick = s_pick >= 0 ? s_pick : s_last;
+        if ((int)tid == pick) {
+            double run = my_excl;
+            uint32_t chosen = start, last_nz = start;
+            bool found = false;
+            for (uint32_t i = 0; i < seg; ++i) {
+                const double p = abs2(src[start + i]);
+                if (p > 0.0) last_nz = start + i;
+                run += p;
+                if (!found && run > resid && p > 0.0) {
+                    chosen = start + i;
+                    found = true;
+                }
+            }
+            indices[shot] = (c << cb) | (uint64_t)(found ? chosen : last_nz);
+        }
+        if (pick < 0 && tid == 0) indices[shot] = (c << cb);  // all-zero chunk: cannot happen for a normalised state
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ big dense matrix (correctness path)
+struct BigDesc {
+    int k;
+    int8_t tgt[16];
+};
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+    matrix_big_kernel(const typename Traits<real>::vec *__restrict__ src, typename Traits<real>::vec *__restrict__ dst,
+                      const uint64_t size, const uint64_t hi_base, const typename Traits<real>::vec *__restrict__ M,
+                      const BigDesc bd, const uint64_t cmask, const uint64_t cval) {
+    using vec = typename Traits<real>::vec;
+    extern __shared__ uint64_t dep[];  // column -> physical offset
+    const uint32_t D = 1u << bd.k;
+    uint64_t tmask = 0;
+    for (int t = 0; t < bd.k; ++t) tmask |= 1ull << bd.tgt[t];
+    for (uint32_t c = threadIdx.x; c < D; c += blockDim.x) {
+        uint64_t v = 0;
+        for (int t = 0; t < bd.k; ++t) v |= (uint64_t)((c >> t) & 1u) << bd.tgt[t];
+        dep[c] = v;
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += stride) {
+        if ((((hi_base | i) ^ cval) & cmask) != 0) {
+            dst[i] = src[i];
+            continue;
+        }
+        uint32_t row = 0;
+        for (int t = 0; t < bd.k; ++t) row |= (uint32_t)((i >> bd.tgt[t]) & 1ull) << t;
+        const uint64_t base = i & ~tmask;
+        const vec *mrow = M + (size_t)row * D;
+        real ar = 0, ai = 0;
+        for (uint32_t c = 0; c < D; ++c) {
+            const vec m = mrow[c];
+            const vec x = src[base | dep[c]];
+            ar = fma(m.x, x.x, ar);
+            ar = fma(-m.y, x.y, ar);
+            ai = fma(m.x, x.y, ai);
+            ai = fma(m.y, x.x, ai);
+        }
+        vec o;
+        o.x = ar;
+        o.y = ai;
+        dst[i] = o;
+    }
+}
+
+unsigned grid_for(uint64_t items, unsigned threads, unsigned per_sm) {
+    uint64_t blocks = (items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)sm_count() * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+}  // namespace
+
+int launch_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, cudaStream_t s) {
+    if (!src || !dst || !perm || n < 1 || n > 40 || src == dst)
+        return set_error(QB2_EINVAL, "qb2_permute_bits: bad arguments");
+    uint64_t seen = 0;
+    for (int p = 0; p < n; ++p) {
+        if (perm[p] < 0 || perm[p] >= n || ((seen >> perm[p]) & 1)) return set_error(QB2_EINVAL, "qb2_permute_bits: not a permutation");
+        seen |= 1ull << perm[p];
+    }
+    // bit p of i (source) = bit perm[p] of j (destination): i = sum ((j >> perm[p]) & 1) << p, merged into runs
+    BitRuns r;
+    r.n = 0;
+    int p = 0;
+    while (p < n) {
+        int len = 1;
+        while (p + len < n && perm[p + len] == perm[p] + len) ++len;
+        r.src[r.n] = (uint8_t)perm[p];
+        r.dst[r.n] = (uint8_t)p;
+        r.len[r.n] = (uint8_t)len;
+        ++r.n;
+        p += len;
+    }
+    const uint64_t size = 1ull << n;
+    const unsigned grid = grid_for(size, 256, 16);
+    if (dtype == QB2_C64)
+        permute_bits_kernel<float2><<<grid, 256, 0, s>>>((const float2 *)src, (float2 *)dst, size, r);
+    else
+        permute_bits_kernel<double2><<<grid, 256, 0, s>>>((const double2 *)src, (double2 *)dst, size, r);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "permute_bits launch");
+}
+
+int launch_norm2(const void *state, int n, double *out_dev, int dtype, cudaStream_t s) {
+    if (!state || !out_dev || n < 0 || n > 40) return set_error(QB2_EINVAL, "qb2_norm2: bad arguments");
+    QB2_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), s));
+    const uint64_t size = 1ull << n;
+    const unsigned grid = grid_for(size, 256, 8);
+    if (dtype == QB2_C64)
+        norm2_kernel<float2><<<grid, 256, 0, s>>>((const float2 *)state, size, out_dev);
+    else
+        norm2_kernel<double2><<<grid, 256, 0, s>>>((const double2 *)state, size, out_dev);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "norm2 launch");
+}
+
+int launch_probabilities(const void *state, int n, uint64_t hi_base, const int *mes_pos, int m, double *probs_dev,
+                         int dtype, cudaStream_t s) {
+    if (!state || !probs_dev || n < 1 || n > 40 || m < 0 || m > 62 || (m > 0 && !mes_pos))
+        return set_error(QB2_EINVAL, "qb2_probabilities: bad arguments");
+    MesDesc md;
+    md.m = m;
+    uint64_t seen = 0;
+    for (int k = 0; k < m; ++k) {
+        if (mes_pos[k] < 0 || mes_pos[k] > 62 || ((seen >> mes_pos[k]) & 1))
+            return set_error(QB2_EINVAL, "qb2_probabilities: bad or duplicate position %d", mes_pos[k]);
+        seen |= 1ull << mes_pos[k];
+        md.pos[k] = (int8_t)mes_pos[k];
+    }
+    const int C = n < PROB_CHUNK_BITS ? n : PROB_CHUNK_BITS;
+    const uint64_t nchunks = 1ull << (n - C);
+    uint64_t blocks = nchunks;
+    const uint64_t cap = (uint64_t)sm_count() * 6;
+    if (blocks > cap) blocks = cap;
+    const size_t smem = sizeof(double) << C;
+    if (dtype == QB2_C64)
+        probabilities_kernel<float2><<<(unsigned)blocks, PROB_THREADS, smem, s>>>((const float2 *)state, n, C, hi_base, md, probs_dev);
+    else
+        probabilities_kernel<double2><<<(unsigned)blocks, PROB_THREADS, smem, s>>>((const double2 *)state, n, C, hi_base, md, probs_dev);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "probabilities launch");
+}
+
+int sample_chunk_bits(int n) {
+    int cb = n < 12 ? n : 12;
+    if (n - 18 > cb) cb = n - 18;
+    return cb;
+}
+
+int launch_sample_prepare(const void *state, int n, double *chunk_sums_dev, int dtype, cudaStream_t s) {
+    if (!state || !chunk_sums_dev || n < 0 || n > 40) return set_error(QB2_EINVAL, "qb2_sample_prepare: bad arguments");
+    const int cb = sample_chunk_bits(n);
+    const uint64_t nchunks = 1ull << (n - cb);
+    uint64_t blocks = nchunks;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (dtype == QB2_C64)
+        chunk_sums_kernel<float2><<<(unsigned)blocks, SAMPLE_THREADS, 0, s>>>((const float2 *)state, cb, nchunks, chunk_sums_dev);
+    else
+        chunk_sums_kernel<double2><<<(unsigned)blocks, SAMPLE_THREADS, 0, s>>>((const double2 *)state, cb, nchunks, chunk_sums_dev);
+    count_launch();
+    QB2_CUDA(cudaGetLastError());
+    scan_kernel<<<1, 1024, 0, s>>>(chunk_sums_dev, nchunks);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "sample_prepare launch");
+}
+
+int launch_sample_draw(const void *state, int n, const double *chunk_sums_dev, const double *uniforms_dev,
+                       int64_t shots, uint64_t *indices_dev, int dtype, cudaStream_t s) {
+    if (!state || !chunk_sums_dev || !uniforms_dev || !indices_dev || n < 0 || n > 40 || shots < 0)
+        return set_error(QB2_EINVAL, "qb2_sample_draw: bad arguments");
+    if (shots == 0) return QB2_OK;
+    const int cb = sample_chunk_bits(n);
+    const uint64_t nchunks = 1ull << (n - cb);
+    uint64_t blocks = (uint64_t)shots;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (dtype == QB2_C64)
+        sample_draw_kernel<float2><<<(unsigned)blocks, SAMPLE_THREADS, 0, s>>>((const float2 *)state, cb, nchunks, chunk_sums_dev, uniforms_dev, shots, indices_dev);
+    else
+        sample_draw_kernel<double2><<<(unsigned)blocks, SAMPLE_THREADS, 0, s>>>((const double2 *)state, cb, nchunks, chunk_sums_dev, uniforms_dev, shots, indices_dev);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "sample_draw launch");
+}
+
+int launch_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev, const int *targets,
+                      int k, uint64_t cmask, uint64_t cval, int dtype, cudaStream_t s) {
+    if (!src || !dst || src == dst || !matrix_dev || !targets || n < 1 || n > 40)
+        return set_error(QB2_EINVAL, "qb2_apply_matrix_big: bad arguments");
+    if (k < 1 || k > 10 || k > n) return set_error(QB2_ELIMIT, "qb2_apply_matrix_big: k=%d outside 1..10", k);
+    BigDesc bd;
+    bd.k = k;
+    uint64_t seen = 0;
+    for (int t = 0; t < k; ++t) {
+        if (targets[t] < 0 || targets[t] >= n || ((seen >> targets[t]) & 1))
+            return set_error(QB2_EINVAL, "qb2_apply_matrix_big: bad target %d", targets[t]);
+        seen |= 1ull << targets[t];
+        bd.tgt[t] = (int8_t)targets[t];
+    }
+    if (cmask & seen) return set_error(QB2_EINVAL, "qb2_apply_matrix_big: control on a target");
+    const uint64_t size = 1ull << n;
+    const unsigned grid = grid_for(size, 256, 8);
+    const size_t smem = sizeof(uint64_t) << k;
+    if (dtype == QB2_C64)
+        matrix_big_kernel<float><<<grid, 256, smem, s>>>((const float2 *)src, (float2 *)dst, size, hi_base, (const float2 *)matrix_dev, bd, cmask, cval);
+    else
+        matrix_big_kernel<double><<<grid, 256, smem, s>>>((const double2 *)src, (double2 *)dst, size, hi_base, (const double2 *)matrix_dev, bd, cmask, cval);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "matrix_big launch");
+}
+
+}  // namespace qb2

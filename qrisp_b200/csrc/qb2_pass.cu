@@ -1,0 +1,423 @@
+// qb2_pass.cu -- the fused multi-gate pass kernel (see include/qrisp_b200.h).
+//
+// Replaces the reference's per-gate tensor contraction (tensor_factor.py:67-89 ->
+// bi_arrays.py:1175-1299 `tensordot`, which reshapes, transposes and multiplies the whole
+// state once per gate) by ONE streaming sweep per group of gates:
+//
+//   global --(coalesced 128 B lines)--> registers --ops--> [smem exchange --ops-->]* --> global
+//
+// Every thread owns 2**r amplitudes in registers.  Gates whose dense targets are register
+// bits are pure register arithmetic (fully unrolled, so all register indices are compile
+// time constants).  A smem "exchange" re-distributes the tile so that other tile positions
+// become register bits; its slot map is an XOR-linear function of the thread id chosen by
+// the host so that both the store and the load side are bank-conflict free.
+//
+// HBM-bound by construction: algorithmic bytes per launch = 2 * 2**n * sizeof(amplitude).
+#include <type_traits>
+
+#include "qb2_internal.cuh"
+
+namespace qb2 {
+
+namespace {
+
+constexpr int ROOT_BITS = 8;
+constexpr int NROOT = 1 << ROOT_BITS;
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// compile-time bookkeeping for a gate on register bits P0 < P1 < ... (K of them)
+template <int RB, int K, int P0, int P1, int P2, int P3>
+struct BitMap {
+    __host__ __device__ static constexpr int pos(int i) { return i == 0 ? P0 : i == 1 ? P1 : i == 2 ? P2 : P3; }
+    __host__ __device__ static constexpr int tmask() {
+        int m = 0;
+        for (int i = 0; i < K; ++i) m |= 1 << pos(i);
+        return m;
+    }
+    // matrix index t -> register index bits (matrix bit i <-> register bit pos(i))
+    __host__ __device__ static constexpr int dep(int t) {
+        int v = 0;
+        for (int i = 0; i < K; ++i) v |= ((t >> i) & 1) << pos(i);
+        return v;
+    }
+    // group number g -> register index with the target bits clear
+    __host__ __device__ static constexpr int base(int g) {
+        int b = 0, gi = 0;
+        for (int p = 0; p < RB; ++p)
+            if (!((tmask() >> p) & 1)) {
+                b |= ((g >> gi) & 1) << p;
+                ++gi;
+            }
+        return b;
+    }
+};
+
+template <typename real, int RB, int K, int P0, int P1 = -1, int P2 = -1, int P3 = -1>
+__device__ __forceinline__ void apply_mat(real (&re)[1 << RB], real (&im)[1 << RB], const real *__restrict__ m,
+                                          const uint32_t jmask) {
+    using BM = BitMap<RB, K, P0, P1, P2, P3>;
+    constexpr int D = 1 << K;
+    constexpr int NG = (1 << RB) / D;
+    static_for<0, NG>([&](auto G) {
+        constexpr int base = BM::base(decltype(G)::value);
+        if ((jmask >> base) & 1u) {
+            real xr[D], xi[D];
+            static_for<0, D>([&](auto C) {
+                constexpr int j = base | BM::dep(decltype(C)::value);
+                xr[decltype(C)::value] = re[j];
+                xi[decltype(C)::value] = im[j];
+            });
+            static_for<0, D>([&](auto Rw) {
+                constexpr int row = decltype(Rw)::value;
+                real ar = 0, ai = 0;
+                static_for<0, D>([&](auto C) {
+                    constexpr int col = decltype(C)::value;
+                    const real mr = m[2 * (row * D + col)];
+                    const real mi = m[2 * (row * D + col) + 1];
+                    ar = fma(mr, xr[col], ar);
+                    ar = fma(-mi, xi[col], ar);
+                    ai = fma(mr, xi[col], ai);
+                    ai = fma(mi, xr[col], ai);
+                });
+                constexpr int j = base | BM::dep(row);
+                re[j] = ar;
+                im[j] = ai;
+            });
+        }
+    });
+}
+
+// exp(2 pi i * turns / 2**32): 8 high bits from a table of exact roots, the centred low
+// 24 bits through a short Taylor series (|theta| <= pi/256: the dropped terms are < 1e-9).
+__device__ __forceinline__ float2 unit_phase(const uint32_t turns, const float2 *__restrict__ roots) {
+    const uint32_t s = turns + (1u << 23);
+    const uint32_t k = s >> 24;
+    const int low = (int)(s & 0xFFFFFFu) - (1 << 23);
+    const float th = (float)low * 1.4629180792671596e-9f;  // 2 pi / 2**32
+    const float t2 = th * th;
+    const float c = fmaf(-0.5f, t2, 1.0f);
+    const float sn = fmaf(th * t2, -0.16666667f, th);
+    const float2 w = roots[k];
+    return make_float2(fmaf(w.x, c, -w.y * sn), fmaf(w.x, sn, w.y * c));
+}
+
+__device__ __forceinline__ double2 unit_phase(const uint64_t turns, const double2 *) {
+    double s, c;
+    sincospi((double)(int64_t)turns * 0x1p-63, &s, &c);
+    return make_double2(c, s);
+}
+
+__device__ __forceinline__ uint32_t tab_index(const qb2_tab &t, const uint64_t x) {
+    uint32_t idx = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const qb2_piece pc = t.p[p];
+        if (pc.len != 0) idx |= ((uint32_t)(x >> pc.shift) & ((1u << pc.len) - 1u)) << pc.out;
+    }
+    return idx;
+}
+
+template <typename V>
+__device__ __forceinline__ V ld_stream(const V *p) {
+    return __ldcs(p);
+}
+template <typename V>
+__device__ __forceinline__ void st_stream(V *p, const V v) {
+    __stcs(p, v);
+}
+
+template <typename real, int RB, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+    pass_kernel(typename Traits<real>::vec *__restrict__ state, const uint8_t *__restrict__ blob,
+                const uint64_t hi_base, const uint32_t ntiles, const uint32_t small_bytes, const uint32_t roots_off,
+                const uint32_t tile_off) {
+    using vec = typename Traits<real>::vec;
+    using frac = typename Traits<real>::frac;
+    constexpr int NR = 1 << RB;
+    extern __shared__ __align__(16) uint8_t smem[];
+
+    const uint32_t tid = threadIdx.x;
+    // ---- stage the small section (header, phases, ops, coefficients, index arrays)
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        for (uint32_t i = tid; i < small_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    vec *const roots = reinterpret_cast<vec *>(smem + roots_off);
+    if constexpr (std::is_same<real, float>::value) {
+        for (uint32_t i = tid; i < NROOT; i += blockDim.x) {
+            float s, c;
+            sincospif((float)i * (2.0f / NROOT), &s, &c);
+            roots[i] = make_float2(c, s);
+        }
+    }
+    __syncthreads();
+
+    const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(smem);
+    const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(smem + H->phases_off);
+    const qb2_op *const ops = reinterpret_cast<const qb2_op *>(smem + H->ops_off);
+    const real *const coefs = reinterpret_cast<const real *>(smem + H->coef_off);
+    const uint16_t *const a16 = reinterpret_cast<const uint16_t *>(smem + H->u16_off);
+    const uint64_t *const a64 = reinterpret_cast<const uint64_t *>(smem + H->u64_off);
+    const qb2_tab *const tabs = reinterpret_cast<const qb2_tab *>(smem + H->tabdesc_off);
+    const frac *const tables = reinterpret_cast<const frac *>(blob + H->tab_off);
+    vec *const tile = reinterpret_cast<vec *>(smem + tile_off);
+    const int TB = (int)H->T - RB;  // thread bits
+    const uint32_t n_phases = H->n_phases;
+    const int n_seg = H->n_seg;
+
+    real re[NR], im[NR];
+
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        // ---- physical offset of the tile (tile id bits deposited into the non-tile positions)
+        uint64_t tbase = 0;
+        for (int s = 0; s < n_seg; ++s) {
+            const qb2_seg sg = H->seg[s];
+            tbase |= (uint64_t)((t >> sg.src) & ((1u << sg.len) - 1u)) << sg.dst;
+        }
+        // ---- phase 0: load
+        uint64_t xloc;  // local physical index of this thread's register 0
+        {
+            const qb2_phase &ph = phases[0];
+            uint64_t xt = 0;
+            for (int b = 0; b < TB; ++b)
+                if ((tid >> b) & 1u) xt |= a64[ph.pcol + b];
+            xloc = tbase | xt;
+            const uint64_t *rp = a64 + ph.rphys;
+            static_for<0, NR>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                const vec v = ld_stream(state + (xloc | rp[j]));
+                re[j] = v.x;
+                im[j] = v.y;
+            });
+        }
+        for (uint32_t p = 0; p < n_phases; ++p) {
+            const qb2_phase &ph = phases[p];
+            if (p > 0) {
+                // ---- exchange through shared memory
+                {
+                    const uint16_t *xw = a16 + ph.xw;
+                    uint32_t wb = 0;
+                    for (int b = 0; b < TB; ++b)
+                        if ((tid >> b) & 1u) wb ^= xw[b];
+                    static_for<0, NR>([&](auto J) {
+                        constexpr int j = decltype(J)::value;
+                        vec v;
+                        v.x = re[j];
+                        v.y = im[j];
+                        tile[wb ^ xw[TB + j]] = v;
+                    });
+                }
+                __syncthreads();
+                {
+                    const uint16_t *xr = a16 + ph.xr;
+                    uint32_t rb = 0;
+                    uint64_t xt = 0;
+                    for (int b = 0; b < TB; ++b)
+                        if ((tid >> b) & 1u) {
+                            rb ^= xr[b];
+                            xt |= a64[ph.pcol + b];
+                        }
+                    xloc = tbase | xt;
+                    static_for<0, NR>([&](auto J) {
+                        constexpr int j = decltype(J)::value;
+                        const vec v = tile[rb ^ xr[TB + j]];
+                        re[j] = v.x;
+                        im[j] = v.y;
+                    });
+                }
+                __syncthreads();
+            }
+            const uint64_t X = hi_base | xloc;
+            // ---- ops of this phase, on registers
+            for (uint32_t o = ph.first_op; o < ph.first_op + ph.n_ops; ++o) {
+                const qb2_op &op = ops[o];
+                const uint32_t kind = op.kind;
+                if (kind == QB2_OP_DIAG) {
+                    const qb2_tab *tb = tabs + op.data;
+                    frac sum = 0;
+                    const int nthr = op.ntab_thr;
+                    for (int i = 0; i < nthr; ++i) sum += __ldg(tables + tb[i].off + tab_index(tb[i], X));
+                    const int nreg = op.ntab_reg;
+                    if (nreg == 0) {
+                        const vec w = unit_phase(sum, roots);
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            const real xr_ = re[j], xi_ = im[j];
+                            re[j] = fma(xr_, w.x, -xi_ * w.y);
+                            im[j] = fma(xr_, w.y, xi_ * w.x);
+                        });
+                    } else {
+                        tb += nthr;
+                        const frac *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
+                        const uint16_t *g0 = a16, *g1 = a16, *g2 = a16, *g3 = a16;
+                        t0 = tables + tb[0].off + tab_index(tb[0], X);
+                        g0 = a16 + tb[0].regoff;
+                        if (nreg > 1) {
+                            t1 = tables + tb[1].off + tab_index(tb[1], X);
+                            g1 = a16 + tb[1].regoff;
+                        }
+                        if (nreg > 2) {
+                            t2 = tables + tb[2].off + tab_index(tb[2], X);
+                            g2 = a16 + tb[2].regoff;
+                        }
+                        if (nreg > 3) {
+                            t3 = tables + tb[3].off + tab_index(tb[3], X);
+                            g3 = a16 + tb[3].regoff;
+                        }
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            frac s = sum + __ldg(t0 + g0[j]);
+                            if (nreg > 1) s += __ldg(t1 + g1[j]);
+                            if (nreg > 2) s += __ldg(t2 + g2[j]);
+                            if (nreg > 3) s += __ldg(t3 + g3[j]);
+                            const vec w = unit_phase(s, roots);
+                            const real xr_ = re[j], xi_ = im[j];
+                            re[j] = fma(xr_, w.x, -xi_ * w.y);
+                            im[j] = fma(xr_, w.y, xi_ * w.x);
+                        });
+                    }
+                } else if (((X ^ op.cval) & op.cmask) == 0) {
+                    const real *m = coefs + 2 * (size_t)op.data;
+                    const uint32_t jmask = op.jmask;
+                    const int b0 = op.b0, b1 = op.b1;
+                    if (kind == QB2_OP_MAT1) {
+                        static_for<0, RB>([&](auto B) {
+                            if (b0 == decltype(B)::value) apply_mat<real, RB, 1, decltype(B)::value>(re, im, m, jmask);
+                        });
+                    } else if (kind == QB2_OP_MAT2) {
+                        static_for<0, RB>([&](auto B0) {
+                            static_for<decltype(B0)::value + 1, RB>([&](auto B1) {
+                                if (b0 == decltype(B0)::value && b1 == decltype(B1)::value)
+                                    apply_mat<real, RB, 2, decltype(B0)::value, decltype(B1)::value>(re, im, m, jmask);
+                            });
+                        });
+                    } else if (kind == QB2_OP_MAT3) {
+                        if constexpr (RB >= 3) apply_mat<real, RB, 3, 0, 1, 2>(re, im, m, jmask);
+                    } else if (kind == QB2_OP_MAT4) {
+                        if constexpr (RB >= 4) apply_mat<real, RB, 4, 0, 1, 2, 3>(re, im, m, jmask);
+                    }
+                }
+            }
+        }
+        // ---- store with the last phase's distribution
+        {
+            const uint64_t *rp = a64 + phases[n_phases - 1].rphys;
+            static_for<0, NR>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                vec v;
+                v.x = re[j];
+                v.y = im[j];
+                st_stream(state + (xloc | rp[j]), v);
+            });
+        }
+    }
+}
+
+template <typename real>
+__global__ void init_basis_kernel(typename Traits<real>::vec *__restrict__ state, const uint64_t size,
+                                  const uint64_t basis) {
+    using vec = typename Traits<real>::vec;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += stride) {
+        vec v;
+        v.x = (i == basis) ? (real)1 : (real)0;
+        v.y = 0;
+        state[i] = v;
+    }
+}
+
+struct Variant {
+    const void *fn;
+    int rb, maxt;
+    bool attr_set;
+};
+
+template <typename real, int RB, int MAXT, int MINB>
+int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
+                   cudaStream_t s) {
+    using vec = typename Traits<real>::vec;
+    auto kern = pass_kernel<real, RB, MAXT, MINB>;
+    static bool attr_set = false;
+    static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
+    const uint32_t threads = 1u << (h->T - RB);
+    const uint32_t roots_off = (h->small_bytes + 15u) & ~15u;
+    const uint32_t tile_off = roots_off + (std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0);
+    const size_t tile_bytes = h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0;
+    const size_t smem = tile_off + tile_bytes;
+    if (!attr_set) {
+        QB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    if (smem > 200 * 1024) return set_error(QB2_ELIMIT, "pass needs %zu bytes of shared memory", smem);
+    if (occ_cache_threads != (int)threads || occ_cache_smem != (int)smem) {
+        int occ = 0;
+        QB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (int)threads, smem));
+        if (occ < 1) return set_error(QB2_ELIMIT, "pass kernel does not fit on an SM (threads=%u smem=%zu)", threads, smem);
+        occ_cache = occ;
+        occ_cache_threads = (int)threads;
+        occ_cache_smem = (int)smem;
+    }
+    uint32_t grid = (uint32_t)(occ_cache * sm_count());
+    if (grid > ntiles) grid = ntiles;
+    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), reinterpret_cast<const uint8_t *>(blob_dev), hi_base,
+                                     ntiles, h->small_bytes, roots_off, tile_off);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "pass_kernel launch");
+}
+
+}  // namespace
+
+int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, int dtype,
+                cudaStream_t s) {
+    if (!state || !h || !blob_dev) return set_error(QB2_EINVAL, "qb2_run_pass: null pointer");
+    if (h->magic != QB2_PASS_MAGIC) return set_error(QB2_EINVAL, "qb2_run_pass: bad magic 0x%08x", h->magic);
+    if ((int)h->dtype != dtype) return set_error(QB2_EINVAL, "qb2_run_pass: pass dtype %d != state dtype %d", h->dtype, dtype);
+    if ((int)h->n != n) return set_error(QB2_EINVAL, "qb2_run_pass: pass built for n=%u, state has n=%d", h->n, n);
+    if (h->T > QB2_MAX_TILE_BITS || h->T > n || h->r > h->T || h->r > QB2_MAX_REG_BITS)
+        return set_error(QB2_ELIMIT, "qb2_run_pass: T=%u r=%u n=%d outside limits", h->T, h->r, n);
+    if (h->n_seg > QB2_MAX_SEGS) return set_error(QB2_ELIMIT, "qb2_run_pass: too many segments");
+    if (h->small_bytes > QB2_MAX_SMALL_BYTES || (h->small_bytes & 15u) || h->small_bytes < sizeof(qb2_pass_header))
+        return set_error(QB2_ELIMIT, "qb2_run_pass: small section of %u bytes", h->small_bytes);
+    if (h->n_phases < 1) return set_error(QB2_EINVAL, "qb2_run_pass: pass without phases");
+    if (((uintptr_t)blob_dev & 15u) != 0) return set_error(QB2_EINVAL, "qb2_run_pass: blob not 16-byte aligned");
+    if (n - (int)h->T > 31) return set_error(QB2_ELIMIT, "qb2_run_pass: too many tiles");
+    const uint32_t ntiles = 1u << (n - h->T);
+    const int tb = h->T - h->r;
+    if (dtype == QB2_C64) {
+        if (h->r == 4 && tb <= 8) return launch_variant<float, 4, 256, 4>(state, hi_base, h, blob_dev, ntiles, s);
+        if (h->r == 4 && tb == 9) return launch_variant<float, 4, 512, 2>(state, hi_base, h, blob_dev, ntiles, s);
+        if (h->r == 5 && tb <= 8) return launch_variant<float, 5, 256, 2>(state, hi_base, h, blob_dev, ntiles, s);
+        if (h->r == 3 && tb <= 8) return launch_variant<float, 3, 256, 6>(state, hi_base, h, blob_dev, ntiles, s);
+    } else if (dtype == QB2_C128) {
+        if (h->r == 3 && tb <= 8) return launch_variant<double, 3, 256, 4>(state, hi_base, h, blob_dev, ntiles, s);
+        if (h->r == 4 && tb <= 8) return launch_variant<double, 4, 256, 2>(state, hi_base, h, blob_dev, ntiles, s);
+    }
+    return set_error(QB2_ELIMIT, "qb2_run_pass: no kernel variant for dtype=%d r=%u T=%u", dtype, h->r, h->T);
+}
+
+int launch_init_basis(void *state, int n, uint64_t basis, int dtype, cudaStream_t s) {
+    if (!state || n < 0 || n > 40) return set_error(QB2_EINVAL, "qb2_init_basis: bad arguments");
+    const uint64_t size = 1ull << n;
+    if (basis != QB2_NO_BASIS && basis >= size) return set_error(QB2_EINVAL, "qb2_init_basis: basis out of range");
+    uint64_t blocks = (size + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == QB2_C64)
+        init_basis_kernel<float><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float2 *>(state), size, basis);
+    else if (dtype == QB2_C128)
+        init_basis_kernel<double><<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<double2 *>(state), size, basis);
+    else
+        return set_error(QB2_EINVAL, "qb2_init_basis: bad dtype %d", dtype);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "init_basis launch");
+}
+
+}  // namespace qb2

@@ -1,0 +1,646 @@
+"""Pass planner: normalised ops -> packed passes for ``qb2_run_pass`` (include/qrisp_b200.h).
+
+This is the B200 replacement of the reference's circuit preprocessing for simulation
+(reference: circuit_preprocessing.py:119-157 ``group_qc`` and :840-852
+``circuit_preprocessor``).  The reference groups gates so that fewer, larger dense matrices
+are multiplied into the state; here gates are grouped so that the state makes as few trips
+through HBM as possible:
+
+* a PASS is a set of ops whose dense targets fit into one tile of ``T`` physical positions
+  (the lowest ``L`` positions are always part of the tile so that every global access is a
+  full 128-byte line);
+* inside a pass, a PHASE is a set of ops whose dense targets fit into the ``r`` register
+  positions of the phase; between phases the tile is re-distributed through shared memory;
+* diagonal ops and controls never constrain anything: they are evaluated from the physical
+  index, wherever the qubit lives (tile, other tile, other rank).
+
+The planner also owns the qubit-permutation schedule: ``pos[q]`` is the physical position of
+logical qubit ``q``; an exact SWAP only edits that map.
+
+Everything here is host logic on small arrays; nothing touches amplitudes.
+"""
+
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+from .normalize import CMat, DiagTerm, Relabel
+
+QB2_PASS_MAGIC = 0x32425151
+QB2_C64, QB2_C128 = 0, 1
+OP_MAT = {1: 1, 2: 2, 3: 3, 4: 4}
+OP_DIAG = 5
+MAX_SEGS = 16
+MAX_SMALL_BYTES = 24576
+MAX_TAB_BITS = 10
+MAX_PIECES = 6
+MAX_REG_TABS = 4
+HEADER_BYTES = 128
+
+
+class PlanConfig:
+    """Tile geometry.  ``T`` tile bits, ``r`` register bits, ``L`` forced low positions."""
+
+    def __init__(self, n, dtype=QB2_C64, T=None, r=None, L=4):
+        self.dtype = dtype
+        if r is None:
+            r = 4 if dtype == QB2_C64 else 3
+        if T is None:
+            T = r + 8
+        T = min(T, n)
+        r = min(r, T)
+        self.n, self.T, self.r = n, T, r
+        self.L = min(L, T - r) if T - r >= 1 else 0
+        # lanes that one shared-memory wavefront covers: 16 for 8-byte, 8 for 16-byte amplitudes
+        self.conflict_bits = 4 if dtype == QB2_C64 else 3
+        self.max_mat = min(self.r, 4)  # widest dense op the pass kernel applies in registers
+
+    @property
+    def TB(self):
+        return self.T - self.r
+
+
+class BigMatStep:
+    """A dense unitary too wide for a pass: runs through ``qb2_apply_matrix_big``."""
+
+    kind = "big"
+
+    def __init__(self, positions, matrix, cmask, cval):
+        self.positions, self.matrix, self.cmask, self.cval = positions, matrix, cmask, cval
+
+
+class DescriptorOverflow(RuntimeError):
+    pass
+
+
+class PassStep:
+    kind = "pass"
+
+    def __init__(self, blob, n_ops, n_phases, tile_pos, n_gate_ops):
+        self.blob, self.n_ops, self.n_phases, self.tile_pos = blob, n_ops, n_phases, tile_pos
+        self.n_gate_ops = n_gate_ops
+
+
+# ----------------------------------------------------------------------------------------
+# scheduling
+# ----------------------------------------------------------------------------------------
+
+
+def _commuting_pick(ops, accept):
+    """Generic list scheduler: walk ``ops`` in order, take every op that ``accept`` takes and
+    that commutes with everything skipped so far; return (taken, rest)."""
+    taken, rest = [], []
+    blocked_nd, blocked_d = set(), set()
+    for op in ops:
+        ok = True
+        for q in op.nd:
+            if q in blocked_nd or q in blocked_d:
+                ok = False
+                break
+        if ok:
+            for q in op.d:
+                if q in blocked_nd:
+                    ok = False
+                    break
+        if ok and accept(op):
+            taken.append(op)
+        else:
+            rest.append(op)
+            blocked_nd.update(op.nd)
+            blocked_d.update(op.d)
+    return taken, rest
+
+
+class Planner:
+    """Turns a list of normalised ops into steps.  ``pos`` is updated in place."""
+
+    def __init__(self, cfg: PlanConfig, pos, n_total=None, window=4096, max_pass_ops=256):
+        self.max_pass_ops = max_pass_ops
+        self.cfg = cfg
+        self.pos = pos  # list: logical qubit -> physical position
+        self.n_total = cfg.n if n_total is None else n_total
+        self.window = window
+
+    # -------------------------------------------------------------- passes
+    def plan(self, ops):
+        """Plan ``ops``.  Returns ``(steps, need)``: ``need`` is None when everything was
+        planned, else the sorted non-local positions the next op needs as dense targets
+        (multi-GPU: the engine swaps them in and calls :meth:`plan` again with
+        ``self.pending``)."""
+        cfg = self.cfg
+        pos = self.pos
+        lowset = set(range(cfg.L))
+        steps = []
+        rest = list(ops)
+        self.pending = []
+        while rest:
+            head, tail = rest[: self.window], rest[self.window :]
+            first = head[0]
+            if first.kind == "mat" and len(first.targets) > cfg.max_mat:
+                tp = [pos[q] for q in first.targets]
+                if any(p >= cfg.n for p in tp):
+                    self.pending = rest
+                    return steps, sorted(p for p in tp if p >= cfg.n)
+                steps.append(self._big_step(first))
+                rest = rest[1:]
+                continue
+            tile_need = set()
+            nonlocal_hit = []
+            resolved = []
+
+            def accept(op):
+                if len(resolved) >= self.max_pass_ops:
+                    return False
+                if op.kind == "relabel":
+                    pos[op.a], pos[op.b] = pos[op.b], pos[op.a]
+                    return True
+                if op.kind == "mat":
+                    if len(op.targets) > cfg.max_mat:
+                        return False
+                    need = {pos[q] for q in op.targets}
+                    if any(p >= cfg.n for p in need):
+                        if not nonlocal_hit:
+                            nonlocal_hit.append(sorted(p for p in need if p >= cfg.n))
+                        return False
+                    need -= lowset
+                    if len(tile_need | need) > cfg.T - cfg.L:
+                        return False
+                    tile_need.update(need)
+                # ops are resolved to positions when accepted: a Relabel accepted later
+                # must not change them
+                resolved.append(self._resolve(op))
+                return True
+
+            taken, rest2 = _commuting_pick(head, accept)
+            if not taken:
+                if nonlocal_hit:
+                    self.pending = rest
+                    return steps, nonlocal_hit[0]
+                raise RuntimeError(f"planner made no progress on {head[0]}")
+            rest = rest2 + tail
+            if resolved:
+                steps.extend(self._build_passes(resolved))
+        return steps, None
+
+    def _build_passes(self, rops):
+        """One pass for ``rops``; if its descriptor outgrows the shared-memory staging
+        area the list is halved (small states put whole circuits into one tile)."""
+        lowset = set(range(self.cfg.L))
+        need = set()
+        for op in rops:
+            if op[0] == "mat":
+                need.update(op[1])
+        need -= lowset
+        if len(need) <= self.cfg.T - self.cfg.L:
+            try:
+                return [self._build_pass(rops, need)]
+            except DescriptorOverflow:
+                pass
+        if len(rops) == 1:
+            raise RuntimeError("a single op does not fit into a pass descriptor")
+        half = len(rops) // 2
+        return self._build_passes(rops[:half]) + self._build_passes(rops[half:])
+
+    def _resolve(self, op):
+        """Replace logical qubits by physical positions (the map may change later)."""
+        pos = self.pos
+        if op.kind == "diag":
+            return ("diag", tuple(pos[q] for q in op.qubits), op.turns)
+        return ("mat", tuple(pos[q] for q in op.targets), op.matrix, {pos[q]: v for q, v in op.controls.items()})
+
+    def _big_step(self, op):
+        pos = self.pos
+        tp = [pos[q] for q in op.targets]
+        cmask = cval = 0
+        for q, v in op.controls.items():
+            cmask |= 1 << pos[q]
+            cval |= int(v) << pos[q]
+        return BigMatStep(tp, op.matrix, cmask, cval)
+
+    # -------------------------------------------------------------- one pass
+    def _build_pass(self, rops, tile_need):
+        cfg = self.cfg
+        tile = set(range(cfg.L)) | set(tile_need)
+        p = 0
+        while len(tile) < cfg.T:
+            if p not in tile:
+                tile.add(p)
+            p += 1
+        tile_pos = sorted(tile)
+        assert len(tile_pos) == cfg.T and tile_pos[-1] < cfg.n
+
+        # ---- phases: greedy, commutation aware
+        phases = []  # (R list, ops)
+        rest = list(rops)
+        while rest:
+            R = []
+            fixed = [None]  # target list of a 3/4-qubit dense op: must sit on register bits 0..k-1
+
+            def accept(op):
+                if op[0] == "diag":
+                    return True
+                tg = op[1]
+                if len(tg) >= 3:
+                    if fixed[0] is not None and fixed[0] != tuple(sorted(tg)):
+                        return False
+                    new = [t for t in tg if t not in R]
+                    if len(R) + len(new) > cfg.r:
+                        return False
+                    fixed[0] = tuple(sorted(tg))
+                    R.extend(new)
+                    return True
+                new = [t for t in tg if t not in R]
+                if len(R) + len(new) > cfg.r:
+                    return False
+                R.extend(new)
+                return True
+
+            taken, rest = _commuting_pick([_RView(o) for o in rest], lambda v: accept(v.op))
+            taken = [v.op for v in taken]
+            rest = [v.op for v in rest]
+            assert taken
+            if fixed[0] is not None:
+                R = list(fixed[0]) + [x for x in R if x not in fixed[0]]
+            phases.append([R, taken])
+
+        # fill register sets, keep the low positions on the lanes for the first / last phase
+        low_lane = set(tile_pos[: min(cfg.conflict_bits, cfg.TB)])
+        for ph in phases:
+            R = ph[0]
+            for cand in reversed(tile_pos):
+                if len(R) >= cfg.r:
+                    break
+                if cand not in R and cand not in low_lane:
+                    R.append(cand)
+            for cand in reversed(tile_pos):
+                if len(R) >= cfg.r:
+                    break
+                if cand not in R:
+                    R.append(cand)
+        default_R = [x for x in reversed(tile_pos) if x not in low_lane][: cfg.r]
+        if len(default_R) < cfg.r:
+            default_R = list(reversed(tile_pos))[: cfg.r]
+        if set(phases[0][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
+            phases.insert(0, [list(default_R), []])
+        if set(phases[-1][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
+            phases.append([list(default_R), []])
+        return self._pack(tile_pos, phases)
+
+    # -------------------------------------------------------------- packing
+    def _pack(self, tile_pos, phases):
+        cfg = self.cfg
+        T, r, TB, n = cfg.T, cfg.r, cfg.TB, cfg.n
+        NR = 1 << r
+        csize = 8 if cfg.dtype == QB2_C64 else 16
+        real_t = np.float32 if cfg.dtype == QB2_C64 else np.float64
+        frac_t = np.uint32 if cfg.dtype == QB2_C64 else np.uint64
+
+        a16, a64, coefs, tabdescs, tables, ops_b, phases_b = [], [], [], [], [], [], []
+        n_tab_entries = 0
+        n_gate_ops = 0
+
+        def add16(vals):
+            off = len(a16)
+            a16.extend(int(v) & 0xFFFF for v in vals)
+            return off
+
+        def add64(vals):
+            off = len(a64)
+            a64.extend(int(v) for v in vals)
+            return off
+
+        prev = None
+        op_count = 0
+        for R, pops in phases:
+            assert len(R) == r and len(set(R)) == r
+            TP = [x for x in tile_pos if x not in R]
+            pcol = add64(1 << x for x in TP)
+            rphys = add64(sum(((j >> i) & 1) << R[i] for i in range(r)) for j in range(NR))
+            xw = xr = 0
+            if prev is not None:
+                col = _slot_columns(tile_pos, prev[1], TP, cfg.conflict_bits)
+                pR, pTP = prev
+                xw = add16([col[x] for x in pTP] + [_xor_cols(col, pR, j) for j in range(NR)])
+                xr = add16([col[x] for x in TP] + [_xor_cols(col, R, j) for j in range(NR)])
+            first_op = op_count
+            # ---- ops: merge runs of diagonal terms
+            i = 0
+            while i < len(pops):
+                op = pops[i]
+                if op[0] == "diag":
+                    terms = []
+                    while i < len(pops) and pops[i][0] == "diag":
+                        terms.append(pops[i])
+                        i += 1
+                    n_gate_ops += len(terms)
+                    for thr_tabs, reg_tabs in _build_tables(terms, R, cfg):
+                        first_tab = len(tabdescs)
+                        for positions, vals in thr_tabs + reg_tabs:
+                            thr_positions = [x for x in positions if x not in R]
+                            reg_positions = [x for x in positions if x in R]
+                            pieces = _pieces(thr_positions)
+                            nthr = len(thr_positions)
+                            regoff = 0
+                            if reg_positions:
+                                regoff = add16(
+                                    sum(((j >> R.index(x)) & 1) << (nthr + k) for k, x in enumerate(reg_positions))
+                                    for j in range(NR)
+                                )
+                            tabdescs.append((pieces, n_tab_entries, regoff))
+                            tables.append(_to_frac(vals, frac_t))
+                            n_tab_entries += len(vals)
+                        ops_b.append(
+                            struct.pack("<QQIIBBBBB3x", 0, 0, 0, first_tab, OP_DIAG, 0, 0, len(thr_tabs), len(reg_tabs))
+                        )
+                        op_count += 1
+                    continue
+                _, tg, mat, ctrls = op
+                n_gate_ops += 1
+                k = len(tg)
+                bits = [R.index(t) for t in tg]
+                order = sorted(range(k), key=lambda a: bits[a])
+                if k >= 3:
+                    assert sorted(bits) == list(range(k)), "3/4-qubit dense ops sit on register bits 0..k-1"
+                m = _permute_matrix(mat, order)
+                sbits = sorted(bits)
+                cmask = cval = 0
+                jmask = 0
+                regc = {R.index(p): v for p, v in ctrls.items() if p in R}
+                for p, v in ctrls.items():
+                    if p not in R:
+                        cmask |= 1 << p
+                        cval |= int(v) << p
+                for j in range(NR):
+                    if all(((j >> b) & 1) == v for b, v in regc.items()):
+                        jmask |= 1 << j
+                data = len(coefs)
+                coefs.extend(m.reshape(-1))
+                ops_b.append(
+                    struct.pack(
+                        "<QQIIBBBBB3x", cmask, cval, jmask, data, OP_MAT[k], sbits[0], sbits[1] if k > 1 else 0, 0, 0
+                    )
+                )
+                op_count += 1
+                i += 1
+            phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, 0, 0))
+            prev = (R, TP)
+
+        # ---- segments: tile id bits -> non-tile local positions
+        segs = []
+        src = 0
+        p = 0
+        nontile = [x for x in range(n) if x not in set(tile_pos)]
+        i = 0
+        while i < len(nontile):
+            j = i
+            while j + 1 < len(nontile) and nontile[j + 1] == nontile[j] + 1:
+                j += 1
+            segs.append((src, nontile[i], j - i + 1))
+            src += j - i + 1
+            i = j + 1
+        if len(segs) > MAX_SEGS:
+            raise RuntimeError("too many tile segments")
+
+        # ---- layout of the small section
+        def align(x, a):
+            return (x + a - 1) // a * a
+
+        off = HEADER_BYTES
+        phases_off = off
+        off += 32 * len(phases_b)
+        ops_off = off
+        off += 32 * len(ops_b)
+        off = align(off, 16)
+        coef_off = off
+        off += csize * len(coefs)
+        off = align(off, 8)
+        u64_off = off
+        off += 8 * len(a64)
+        tabdesc_off = off
+        off += 32 * len(tabdescs)
+        u16_off = off
+        off += 2 * len(a16)
+        small = align(off, 16)
+        if small > MAX_SMALL_BYTES:
+            raise DescriptorOverflow(f"pass descriptor of {small} bytes exceeds the staging limit")
+        tab_off = align(small, 256)
+        total = align(tab_off + n_tab_entries * np.dtype(frac_t).itemsize, 256)
+
+        blob = bytearray(total)
+        hdr = struct.pack(
+            "<IIIIBBBBIIIIIIIII2I",
+            QB2_PASS_MAGIC,
+            total,
+            small,
+            n,
+            T,
+            r,
+            cfg.dtype,
+            len(segs),
+            len(phases_b),
+            phases_off,
+            ops_off,
+            coef_off,
+            u16_off,
+            u64_off,
+            tabdesc_off,
+            tab_off,
+            len(ops_b),
+            0,
+            0,
+        )
+        assert len(hdr) == 64
+        blob[0:64] = hdr
+        for i, (s, d, ln) in enumerate(segs):
+            blob[64 + 4 * i : 68 + 4 * i] = struct.pack("<BBBB", s, d, ln, 0)
+        blob[phases_off : phases_off + 32 * len(phases_b)] = b"".join(phases_b)
+        blob[ops_off : ops_off + 32 * len(ops_b)] = b"".join(ops_b)
+        if coefs:
+            c = np.asarray(coefs, dtype=np.complex128)
+            inter = np.empty(2 * len(c), dtype=real_t)
+            inter[0::2] = c.real
+            inter[1::2] = c.imag
+            blob[coef_off : coef_off + inter.nbytes] = inter.tobytes()
+        if a64:
+            blob[u64_off : u64_off + 8 * len(a64)] = np.asarray(a64, dtype=np.uint64).tobytes()
+        for i, (pieces, toff, regoff) in enumerate(tabdescs):
+            pb = b"".join(struct.pack("<BBBB", s, ln, o, 0) for s, ln, o in pieces)
+            pb += b"\0" * (24 - len(pb))
+            blob[tabdesc_off + 32 * i : tabdesc_off + 32 * i + 32] = pb + struct.pack("<II", toff, regoff)
+        if a16:
+            blob[u16_off : u16_off + 2 * len(a16)] = np.asarray(a16, dtype=np.uint16).tobytes()
+        if tables:
+            tb = np.concatenate(tables)
+            blob[tab_off : tab_off + tb.nbytes] = tb.tobytes()
+        return PassStep(bytes(blob), op_count, len(phases_b), tile_pos, n_gate_ops)
+
+
+class _RView:
+    """Adapter giving a resolved op the ``nd`` / ``d`` interface of the list scheduler
+    (in terms of physical positions)."""
+
+    __slots__ = ("op",)
+
+    def __init__(self, op):
+        self.op = op
+
+    @property
+    def nd(self):
+        return self.op[1] if self.op[0] == "mat" else ()
+
+    @property
+    def d(self):
+        return self.op[1] if self.op[0] == "diag" else tuple(self.op[3].keys())
+
+    @property
+    def kind(self):
+        return self.op[0]
+
+
+# ----------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------
+
+
+def _permute_matrix(mat, order):
+    """New matrix whose index bit ``a`` is the old index bit ``order[a]``."""
+    k = len(order)
+    if order == list(range(k)):
+        return np.asarray(mat, dtype=np.complex128)
+    d = 1 << k
+    idx = np.zeros(d, dtype=np.int64)
+    for a in range(k):
+        idx |= ((np.arange(d) >> a) & 1) << order[a]
+    return np.asarray(mat, dtype=np.complex128)[np.ix_(idx, idx)]
+
+
+def _slot_columns(tile_pos, write_tp, read_tp, conflict_bits):
+    """Shared-memory slot map of an exchange: XOR-linear in the tile-local index.
+
+    Returns ``col[position] -> uint16``; the slot of a tile-local index is the XOR of the
+    columns of its set bits.  The map is built so that the ``2**c`` lanes of a wavefront hit
+    ``2**c`` different bank groups both when the tile is stored under the old distribution
+    (lane bits = ``write_tp[:c]``) and when it is loaded under the new one (``read_tp[:c]``).
+    """
+    c = min(conflict_bits, len(write_tp), len(read_tp))
+    W = list(write_tp[:c])
+    Rr = list(read_tp[:c])
+    col = {}
+    for i, x in enumerate(W):
+        col[x] = 1 << i
+    free_rows = [i for i, x in enumerate(W) if x not in Rr]
+    read_only = [x for x in Rr if x not in W]
+    assert len(free_rows) == len(read_only)
+    nxt = c
+    for x in tile_pos:
+        if x in col:
+            continue
+        col[x] = 1 << nxt
+        nxt += 1
+    for row, x in zip(free_rows, read_only):
+        col[x] ^= 1 << row
+    return col
+
+
+def _xor_cols(col, R, j):
+    v = 0
+    for i, x in enumerate(R):
+        if (j >> i) & 1:
+            v ^= col[x]
+    return v
+
+
+def _pieces(positions):
+    """Runs of consecutive positions -> (shift, len, out) pieces; index bit k <-> positions[k]."""
+    pieces = []
+    i = 0
+    while i < len(positions):
+        j = i
+        while j + 1 < len(positions) and positions[j + 1] == positions[j] + 1:
+            j += 1
+        pieces.append((positions[i], j - i + 1, i))
+        i = j + 1
+    assert len(pieces) <= MAX_PIECES
+    return pieces
+
+
+def _n_runs(positions):
+    return sum(1 for i, x in enumerate(positions) if i == 0 or positions[i - 1] != x - 1)
+
+
+def _to_frac(turns, frac_t):
+    t = np.asarray(turns, dtype=np.float64)
+    t = t - np.floor(t)
+    if frac_t == np.uint32:
+        v = np.rint(t * 4294967296.0)
+        v = np.where(v >= 4294967296.0, 0.0, v)
+        return v.astype(np.uint64).astype(np.uint32)
+    hi = np.floor(t * 4294967296.0)
+    lo = np.rint((t * 4294967296.0 - hi) * 4294967296.0)
+    carry = lo >= 4294967296.0
+    lo = np.where(carry, 0.0, lo)
+    hi = np.where(carry, hi + 1, hi)
+    hi = np.where(hi >= 4294967296.0, 0.0, hi)
+    return (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
+
+
+def _build_tables(terms, R, cfg):
+    """Merge diagonal terms into phase tables.
+
+    Yields ``(thread_tables, register_tables)`` groups, one per DIAG op; every table is
+    ``(sorted positions, turns)`` with the thread/tile positions as the low index bits
+    (ascending, so that neighbouring lanes read neighbouring entries) and the register
+    positions as the high index bits.
+    """
+    Rset = set(R)
+    tabs = []  # [positions(set), list of terms]
+    for _, positions, turns in terms:
+        pset = set(positions)
+        placed = False
+        has_reg = bool(pset & Rset)
+        for tab in tabs:
+            if bool(tab[0] & Rset) != has_reg and len(tab[0] | pset) > len(tab[0]):
+                # do not turn a cheap per-thread table into a per-amplitude one
+                continue
+            u = tab[0] | pset
+            if len(u) <= MAX_TAB_BITS and _n_runs(sorted(x for x in u if x not in Rset)) <= MAX_PIECES:
+                tab[0] = u
+                tab[1].append((positions, turns))
+                placed = True
+                break
+        if not placed:
+            if len(pset) > MAX_TAB_BITS + 2 or _n_runs(sorted(x for x in pset if x not in Rset)) > MAX_PIECES:
+                raise RuntimeError("diagonal term too wide for a phase table")
+            tabs.append([pset, [(positions, turns)]])
+    built = []
+    for pset, tterms in tabs:
+        thr = sorted(x for x in pset if x not in Rset)
+        reg = sorted((x for x in pset if x in Rset), key=R.index)
+        order = thr + reg
+        nb = len(order)
+        idx = np.arange(1 << nb)
+        vals = np.zeros(1 << nb, dtype=np.float64)
+        for positions, turns in tterms:
+            sub = np.zeros(1 << nb, dtype=np.int64)
+            for b, x in enumerate(positions):
+                sub |= ((idx >> order.index(x)) & 1) << b
+            vals += turns[sub]
+        built.append((order, vals, bool(reg)))
+    thr_tabs = [(o, v) for o, v, has in built if not has]
+    reg_tabs = [(o, v) for o, v, has in built if has]
+    groups = []
+    if not reg_tabs:
+        groups.append((thr_tabs, []))
+    else:
+        for s in range(0, len(reg_tabs), MAX_REG_TABS):
+            groups.append((thr_tabs if s == 0 else [], reg_tabs[s : s + MAX_REG_TABS]))
+    # the op encodes the table counts in one byte each
+    out = []
+    for tt, rt in groups:
+        while len(tt) > 200:
+            out.append((tt[:200], []))
+            tt = tt[200:]
+        out.append((tt, rt))
+    return out

@@ -1,0 +1,164 @@
+"""``run`` / ``statevector_sim``: the reference-facing entry points of the B200 path.
+
+Same names, argument meaning and result contract as ``qrisp.simulator.run(qc, shots, token)``
+and ``qrisp.simulator.statevector_sim(qc)`` (reference: simulator.py:44-203 and :220-296):
+a circuit goes in, a counts / probability dict keyed by bitstrings (clbit 0 right-most)
+comes out.  ``qc`` may be a :class:`qrisp_b200.circuit.Circuit` or a Qrisp ``QuantumCircuit``
+(duck-typed through :meth:`Circuit.from_qrisp`).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .circuit import Circuit
+from .engine import StateVector
+from .preprocess import count_measurements, strip_structural, unitarize
+
+# reference: numerics_config.py:24-38
+FLOAT_THRESH = np.float32(1e-5)
+CUTOFF_RATIO = np.float32(2e-4)
+# above this many measured qubits the dense distribution is not materialised on the host;
+# shots are then sampled on the device straight from the amplitudes
+MAX_DENSE_OUTCOME_BITS = 26
+# host<->device bytes of the most recent run()/sample_counts()/statevector_sim() call
+LAST_H2D_BYTES = 0
+LAST_D2H_BYTES = 0
+
+
+def _record_io(sv):
+    global LAST_H2D_BYTES, LAST_D2H_BYTES
+    LAST_H2D_BYTES, LAST_D2H_BYTES = sv.io["h2d"], sv.io["d2h"]
+
+
+def _as_circuit(qc):
+    return qc if isinstance(qc, Circuit) else Circuit.from_qrisp(qc)
+
+
+def prune_outcomes(p):
+    """Which outcomes the reference keeps, and their normalised probabilities.
+
+    reference: bi_arrays.py:1030-1055 -- more than 10 measured qubits: keep
+    ``p > max(p) * cutoff_ratio`` (bi_array_helper.py:315-331); otherwise the recursive
+    halving of bi_array_helper.py:349-387 drops every branch whose norm falls below
+    ``float_thresh``.  tensor_factor.py:184 / quantum_state.py:224 renormalise.
+    """
+    m = int(np.log2(p.size))
+    if m > 10:
+        keep = np.flatnonzero(p > p.max() * CUTOFF_RATIO)
+    else:
+        alive = np.ones(1, dtype=bool)
+        for level in range(m + 1):
+            branch = p.reshape(1 << level, -1).sum(axis=1)
+            alive &= ~(branch < FLOAT_THRESH)
+            if level < m:
+                alive = np.repeat(alive, 2)
+        keep = np.flatnonzero(alive)
+    probs = p[keep]
+    return keep.astype(np.int64), probs / probs.sum()
+
+
+def round_probabilities(cl_prob):
+    """reference: simulator.py:167-169."""
+    cl_prob = np.round(cl_prob, int(-np.log10(np.max(cl_prob))) + 5)
+    return cl_prob / np.sum(cl_prob)
+
+
+def run(qc, shots=None, token="", dtype=np.complex64, seed=None, return_engine=False, **engine_kwargs):
+    """Simulate ``qc`` and return its measurement statistics.
+
+    ``shots=None``: dict ``bitstring -> probability``; ``shots=k``: dict ``bitstring ->
+    count``.  ``token`` is accepted for signature compatibility and ignored, as in the
+    reference.  ``seed`` fixes the sampled counts.
+    """
+    qc = _as_circuit(qc)
+    if len(qc.data) == 0:
+        return {"": shots}
+    if shots == 0:
+        return {}
+    if count_measurements(qc.data) == 0:
+        return {"": 1.0}
+    instrs, n, measurements = unitarize(qc)
+    sv = StateVector(n, dtype=dtype, **engine_kwargs)
+    sv.apply_circuit(instrs)
+    # reference: simulator.py:151-157 -- outcome bit order = descending clbit index
+    measurements.sort(key=lambda x: -x[1])
+    mes_qubits = [q for q, _ in measurements]
+    width = len(mes_qubits)
+    res = {}
+    if width <= MAX_DENSE_OUTCOME_BITS:
+        p = sv.probabilities(mes_qubits)
+        outcomes, probs = prune_outcomes(p)
+        probs = round_probabilities(probs)
+        if shots is None:
+            for o, pr in zip(outcomes, probs):
+                if pr == 0:
+                    continue
+                key = bin(int(o))[2:].zfill(width)
+                res[key] = res.get(key, 0.0) + float(pr)
+        else:
+            rng = np.random.default_rng(seed)
+            samples = rng.choice(len(probs), int(shots), p=probs)
+            hist = np.bincount(samples, minlength=len(probs))
+            for i in np.flatnonzero(hist):
+                res[bin(int(outcomes[i]))[2:].zfill(width)] = int(hist[i])
+    else:
+        if shots is None:
+            raise MemoryError(
+                f"{width} measured qubits: the full distribution has 2**{width} entries; pass shots=... to sample it"
+            )
+        rng = np.random.default_rng(seed)
+        outs = sv.sample(int(shots), mes_qubits, rng=rng)
+        vals, counts = np.unique(outs, return_counts=True)
+        for v, c in zip(vals, counts):
+            res[bin(int(v))[2:].zfill(width)] = int(c)
+    _record_io(sv)
+    if return_engine:
+        return res, sv
+    return res
+
+
+def sample_counts(qc, shots, seed=None, dtype=np.complex64, **engine_kwargs):
+    """Counts sampled ON THE DEVICE from the amplitudes (no dense distribution on the host):
+    the path for wide registers (``get_measurement`` of 30+ qubits)."""
+    qc = _as_circuit(qc)
+    instrs, n, measurements = unitarize(qc)
+    sv = StateVector(n, dtype=dtype, **engine_kwargs)
+    sv.apply_circuit(instrs)
+    measurements.sort(key=lambda x: -x[1])
+    mes_qubits = [q for q, _ in measurements]
+    outs = sv.sample(int(shots), mes_qubits, rng=np.random.default_rng(seed))
+    vals, counts = np.unique(outs, return_counts=True)
+    width = len(mes_qubits)
+    _record_io(sv)
+    return {bin(int(v))[2:].zfill(width): int(c) for v, c in zip(vals, counts)}
+
+
+def statevector_sim(qc, dtype=np.complex64, **engine_kwargs):
+    """The final statevector of a measurement-free circuit, qubit 0 most significant
+    (reference: simulator.py:220-296)."""
+    qc = _as_circuit(qc) if isinstance(qc, Circuit) else Circuit.from_qrisp(qc, transpile=False)
+    if count_measurements(qc.data) != 0:
+        raise Exception("Tried to determine the statevector of a circuit containing a measurement")
+    instrs = strip_structural(qc.data)
+    for i in instrs:
+        if i.matrix is None:
+            raise Exception(f"statevector_sim: non-unitary instruction {i.name!r}")
+    sv = StateVector(qc.num_qubits, dtype=dtype, **engine_kwargs)
+    sv.apply_circuit(instrs)
+    res = sv.statevector()
+    _record_io(sv)
+    return res
+
+
+class B200Backend:
+    """Counterpart of the reference's default backend object (reference:
+    interface/simulators/qrisp_simulator_backend.py ``def_backend``): ``backend.run(qc,
+    shots)`` returns the counts dict."""
+
+    def __init__(self, dtype=np.complex64, **engine_kwargs):
+        self.dtype = dtype
+        self.engine_kwargs = engine_kwargs
+
+    def run(self, qc, shots=None, token=""):
+        return run(qc, shots, token, dtype=self.dtype, **self.engine_kwargs)

@@ -1,0 +1,270 @@
+"""GPU parity tests: the CUDA path (through the C-ABI of libqb2.so) against the oracle, the
+numpy pass emulator and the golden fixtures produced by the reference itself.
+
+Tolerances (north_star): amplitudes and probabilities within 1e-5 absolute at complex64,
+1e-12 at complex128; basis-state labels and qubit order bit-exact; sampled counts consistent
+by a chi-square test.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pass_emulator, ref_sim
+from qrisp_b200.circuit import Circuit, ghz_circuit, ghz_qft_circuit, qft_circuit, random_circuit
+
+from helpers import plan_circuit
+
+pytestmark = pytest.mark.gpu
+
+ATOL64 = 1e-5
+ATOL128 = 1e-12
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    from qrisp_b200 import simulator
+
+    return simulator
+
+
+# ---------------------------------------------------------------------------------------
+# statevectors
+# ---------------------------------------------------------------------------------------
+
+
+def test_golden_statevectors_c64(golden_dir, sim):
+    g = load(golden_dir, "statevector.npz")
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        sv = sim.statevector_sim(qc)
+        assert sv.dtype == np.complex64 and sv.shape == (1 << qc.num_qubits,)
+        np.testing.assert_allclose(sv, g[case + "_sv"], atol=ATOL64, err_msg=case)
+
+
+def test_golden_statevectors_c128(golden_dir, sim):
+    g = load(golden_dir, "statevector.npz")
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        sv = sim.statevector_sim(qc, dtype=np.complex128)
+        want = ref_sim.statevector(qc, dtype=np.complex128)
+        np.testing.assert_allclose(sv, want, atol=ATOL128, err_msg=case)
+
+
+def test_golden_fusion_circuits(golden_dir, sim):
+    g = load(golden_dir, "fusion.npz")
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        np.testing.assert_allclose(sim.statevector_sim(qc), g[case + "_sv"], atol=ATOL64, err_msg=case)
+
+
+@pytest.mark.parametrize("T,r,L", [(9, 4, 4), (10, 3, 4), (11, 4, 5), (12, 4, 4), (13, 5, 4), (13, 4, 4), (12, 5, 6)])
+def test_tile_geometries(sim, T, r, L):
+    qc = random_circuit(15, 5, seed=T * 10 + r, two_qubit="cx")
+    qc.rxx(0.3, 0, 14)
+    qc.mcx([1, 5, 9], 0)
+    qc.swap(2, 11)
+    qc.h(11)
+    sv = sim.statevector_sim(qc, T=T, r=r, L=L)
+    np.testing.assert_allclose(sv, ref_sim.statevector(qc), atol=ATOL64)
+
+
+@pytest.mark.parametrize("dtype,r", [(np.complex128, 3), (np.complex128, 4)])
+def test_c128_geometries(sim, dtype, r):
+    qc = random_circuit(14, 5, seed=r, two_qubit="cx")
+    qc.mcp(0.4, [0, 3, 13], 7)
+    sv = sim.statevector_sim(qc, dtype=dtype, r=r, T=r + 8)
+    np.testing.assert_allclose(sv, ref_sim.statevector(qc, dtype=np.complex128), atol=ATOL128)
+
+
+def test_gpu_matches_emulator_bitwise_layout():
+    """Every packed pass gives the same amplitudes on the GPU as in the numpy emulator
+    (different arithmetic order, so a tolerance; same layout, so no permutation slack)."""
+    import torch
+
+    from qrisp_b200.engine import StateVector
+
+    qc = random_circuit(14, 6, seed=77, two_qubit="cx")
+    qc.cp(0.3, 0, 13)
+    qc.mcx([0, 13], 5)
+    sv = StateVector(14)
+    instrs = [i for i in qc.data if i.matrix is not None]
+    steps, pos, N = plan_circuit(instrs, 14)
+    prog = sv.compile(instrs)
+    assert [len(a.blob) for a in prog.steps] == [len(b.blob) for b in steps]
+    st = np.zeros(1 << 14, dtype=np.complex64)
+    st[0] = 1
+    for a, b in zip(prog.steps, steps):
+        assert a.blob == b.blob  # planning is deterministic
+        st = pass_emulator.run(b.blob, st)
+    prog.run()
+    got = sv.state.cpu().numpy().view(np.complex64)
+    np.testing.assert_allclose(got, st, atol=2e-6)
+
+
+def test_dense_3q_4q_and_big_matrix(sim):
+    rng = np.random.default_rng(5)
+
+    def haar(k):
+        a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        q, _r = np.linalg.qr(a)
+        return q
+
+    qc = Circuit(13)
+    for q in range(13):
+        qc.h(q)
+    qc.unitary(haar(3), (7, 0, 4))
+    qc.unitary(haar(4), (10, 2, 9, 5))
+    qc.unitary(haar(3), (1, 2, 3))
+    qc.unitary(haar(5), (0, 3, 6, 8, 12))
+    qc.unitary(haar(7), (11, 1, 5, 2, 9, 0, 4))
+    qc.cz(0, 1)
+    want = ref_sim.statevector(qc)
+    np.testing.assert_allclose(sim.statevector_sim(qc), want, atol=ATOL64)
+    np.testing.assert_allclose(sim.statevector_sim(qc, T=13, r=5), want, atol=ATOL64)
+    want128 = ref_sim.statevector(qc, dtype=np.complex128)
+    np.testing.assert_allclose(sim.statevector_sim(qc, dtype=np.complex128), want128, atol=ATOL128)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 9, 10])
+def test_small_registers(sim, n):
+    qc = ghz_qft_circuit(n)
+    np.testing.assert_allclose(sim.statevector_sim(qc), ref_sim.statevector(qc), atol=ATOL64)
+    empty = Circuit(n)
+    sv = sim.statevector_sim(empty)
+    assert sv[0] == 1 and np.count_nonzero(sv) == 1
+
+
+def test_medium_width_against_oracle(sim):
+    """22 qubits: still seconds for the numpy oracle, already 2**10 tiles for the kernel."""
+    qc = random_circuit(22, 6, seed=1)
+    np.testing.assert_allclose(sim.statevector_sim(qc), ref_sim.statevector(qc), atol=ATOL64)
+    qc = ghz_qft_circuit(22)
+    np.testing.assert_allclose(sim.statevector_sim(qc), ref_sim.statevector(qc), atol=ATOL64)
+
+
+# ---------------------------------------------------------------------------------------
+# run(): measurement statistics against what the reference returned
+# ---------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz"])
+def test_run_matches_reference_results(golden_dir, sim, fixture):
+    g = load(golden_dir, fixture)
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        got = sim.run(qc, None)
+        ref = {str(k): float(p) for k, p in zip(g[case + "_keys"], g[case + "_probs"])}
+        assert set(got) == set(ref), case  # basis-state labels bit-exact
+        for k in ref:
+            assert abs(got[k] - ref[k]) < ATOL64, (case, k)
+
+
+def test_run_edge_cases(sim):
+    assert sim.run(Circuit(3), 100) == {"": 100}
+    qc = Circuit(2)
+    qc.h(0)
+    assert sim.run(qc, None) == {"": 1.0}
+    qc.measure([0, 1])
+    assert sim.run(qc, 0) == {}
+    res = sim.run(qc, 1000, seed=1)
+    assert set(res) <= {"00", "01"} and sum(res.values()) == 1000
+    with pytest.raises(Exception):
+        sim.statevector_sim(qc)
+
+
+def test_probabilities_and_norm():
+    from qrisp_b200.engine import StateVector
+
+    qc = random_circuit(16, 5, seed=9)
+    psi = ref_sim.statevector(qc, dtype=np.complex128)
+    for dtype, atol in ((np.complex64, 1e-6), (np.complex128, 1e-13)):
+        sv = StateVector(16, dtype=dtype)
+        sv.apply_circuit([i for i in qc.data if i.matrix is not None])
+        assert abs(sv.norm2() - 1.0) < 10 * atol
+        for qubits in ([0], [15], [3, 1, 12], list(range(16)), [15, 0, 7, 8, 2, 5, 11, 13, 1, 14, 3, 9], []):
+            want = ref_sim.marginal_probabilities(psi, qubits, 16)
+            got = sv.probabilities(qubits)
+            np.testing.assert_allclose(got, want, atol=atol, err_msg=str(qubits))
+
+
+def test_sampling_chi_square():
+    """Counts drawn on the device are consistent with the oracle's distribution."""
+    from qrisp_b200.engine import StateVector
+
+    qc = random_circuit(12, 4, seed=4)
+    sv = StateVector(12)
+    sv.apply_circuit([i for i in qc.data if i.matrix is not None])
+    psi = ref_sim.statevector(qc, dtype=np.complex128)
+    qubits = [0, 5, 11, 3, 7]
+    p = ref_sim.marginal_probabilities(psi, qubits, 12)
+    shots = 200000
+    outs = sv.sample(shots, qubits, rng=np.random.default_rng(123))
+    counts = np.bincount(outs.astype(np.int64), minlength=32)
+    chi2 = float(((counts - shots * p) ** 2 / (shots * p)).sum())
+    # 31 degrees of freedom: the 99.99 % quantile is ~66
+    assert chi2 < 70, chi2
+    # the same seed gives the same counts
+    outs2 = sv.sample(shots, qubits, rng=np.random.default_rng(123))
+    assert np.array_equal(outs, outs2)
+    # a basis state is sampled with certainty, with the right label
+    sv2 = StateVector(11)
+    c = Circuit(11)
+    c.x(0), c.x(9)
+    sv2.apply_circuit(c.data)
+    outs = sv2.sample(100, list(range(11)), rng=np.random.default_rng(0))
+    assert np.all(outs == int("10000000010", 2))
+
+
+def test_wide_sampling_path(sim):
+    """More measured qubits than the dense-distribution limit: counts come from the
+    device sampler (GHZ: only all-zeros / all-ones)."""
+    n = 27
+    qc = ghz_circuit(n)
+    qc.measure(list(range(n)))
+    res = sim.run(qc, 2000, seed=3)
+    assert set(res) == {"0" * n, "1" * n}
+    assert sum(res.values()) == 2000 and abs(res["0" * n] - 1000) < 150
+
+
+# ---------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]: 30 qubits, complex64, one B200)
+# ---------------------------------------------------------------------------------------
+
+
+def test_full_size_30_qubits_properties():
+    import torch
+
+    from qrisp_b200.engine import StateVector
+
+    n = 30
+    sv = StateVector(n)
+    # GHZ: exactly two amplitudes of 1/sqrt(2)
+    sv.apply_circuit(ghz_circuit(n).data)
+    assert abs(sv.norm2() - 1.0) < 1e-6
+    st = sv.state.view(-1, 2)
+    assert abs(float(st[0, 0]) - 2**-0.5) < 1e-6 and abs(float(st[-1, 0]) - 2**-0.5) < 1e-6
+    assert int(torch.count_nonzero(st)) == 2
+    # QFT then inverse QFT is the identity (round trip through ~1000 gates)
+    sv.apply_circuit(qft_circuit(n).data)
+    assert abs(sv.norm2() - 1.0) < 1e-5
+    p = sv.probabilities([0, 1, 2])
+    # QFT of GHZ: even outcomes only -> the least significant QFT output bit is 0;
+    sv.apply_circuit(qft_circuit(n, inverse=True).data)
+    st = sv.state.view(-1, 2)
+    assert abs(float(st[0, 0]) - 2**-0.5) < 1e-4 and abs(float(st[-1, 0]) - 2**-0.5) < 1e-4
+    rest = float(sv.norm2()) - float(st[0, 0]) ** 2 - float(st[-1, 0]) ** 2 - float(st[0, 1]) ** 2 - float(st[-1, 1]) ** 2
+    assert abs(rest) < 1e-4
+    assert abs(p.sum() - 1.0) < 1e-6
+    # sampling labels at full width
+    outs = sv.sample(64, list(range(n)), rng=np.random.default_rng(1))
+    assert set(int(o) for o in outs) <= {0, (1 << n) - 1}

@@ -1,0 +1,336 @@
+"""CPU tests of the host logic: gate normalisation, the pass planner and the packed pass
+format, checked through the numpy pass emulator against the oracle and the golden fixtures
+the reference produced."""
+
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pass_emulator, ref_sim
+from qrisp_b200 import preprocess, simulator
+from qrisp_b200.circuit import Circuit, ghz_qft_circuit, qft_circuit, random_circuit
+from qrisp_b200.normalize import CMat, DiagTerm, Relabel, normalize_circuit, normalize_instruction
+
+from helpers import canonical, emulate_statevector, marginal, plan_circuit
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ---------------------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------------------
+
+
+def _ops_unitary(ops, qubits):
+    """Dense unitary (big endian in ``qubits``) of a list of normalised ops."""
+    k = len(qubits)
+    dim = 1 << k
+    u = np.eye(dim, dtype=np.complex128)
+    bit_of = {q: k - 1 - i for i, q in enumerate(qubits)}  # index bit of each qubit
+    perm = list(range(k))
+    for op in ops:
+        if op.kind == "relabel":
+            g = np.zeros((dim, dim))
+            a, b = bit_of[op.a], bit_of[op.b]
+            for x in range(dim):
+                xa, xb = (x >> a) & 1, (x >> b) & 1
+                y = x & ~((1 << a) | (1 << b)) | (xb << a) | (xa << b)
+                g[y, x] = 1
+        elif op.kind == "diag":
+            d = np.zeros(dim, dtype=np.complex128)
+            for x in range(dim):
+                idx = sum(((x >> bit_of[q]) & 1) << i for i, q in enumerate(op.qubits))
+                d[x] = np.exp(2j * np.pi * op.turns[idx])
+            g = np.diag(d)
+        else:
+            g = np.zeros((dim, dim), dtype=np.complex128)
+            for x in range(dim):
+                if all(((x >> bit_of[q]) & 1) == v for q, v in op.controls.items()):
+                    col = sum(((x >> bit_of[q]) & 1) << i for i, q in enumerate(op.targets))
+                    base = x
+                    for q in op.targets:
+                        base &= ~(1 << bit_of[q])
+                    for row in range(1 << len(op.targets)):
+                        y = base | sum(((row >> i) & 1) << bit_of[q] for i, q in enumerate(op.targets))
+                        g[y, x] += op.matrix[row, col]
+                else:
+                    g[x, x] = 1
+        u = g @ u
+    return u
+
+
+def test_normalize_every_golden_gate(golden_dir):
+    g = load(golden_dir, "gates.npz")
+    kinds = {}
+    for name in g["names"]:
+        name = str(name)
+        u = g["op_" + name].astype(np.complex128)
+        k = int(np.log2(u.shape[0]))
+        qubits = tuple(int(q) for q in g["opq_" + name])
+        ops = normalize_instruction(u, qubits)
+        np.testing.assert_allclose(_ops_unitary(ops, list(range(k))), _embed(u, qubits, k), atol=1e-12, err_msg=name)
+        kinds[name] = [o.kind for o in ops]
+    assert kinds["swap"] == ["relabel"]
+    for d in ("z", "s", "t", "p", "rz", "cz", "cp", "crz", "rzz", "mcp", "gphase"):
+        assert kinds[d] == ["diag"], d
+    assert kinds["cx"] == ["mat"] and kinds["mcx"] == ["mat"]
+    # controls are recognised: cx / mcx have ONE dense target
+    u = g["op_mcx"].astype(np.complex128)
+    (op,) = normalize_instruction(u, (0, 1, 2))
+    assert op.targets == (2,) and op.controls == {0: 1, 1: 1}
+
+
+def _embed(u, qubits, k):
+    """u (big endian in qubits) as a k-qubit matrix, big endian in range(k)."""
+    assert sorted(qubits) == list(range(k))
+    t = u.reshape(2 * k * [2])
+    src = list(range(2 * k))
+    dst = [qubits[i] for i in range(k)] + [k + qubits[i] for i in range(k)]
+    return np.moveaxis(t, src, dst).reshape(1 << k, 1 << k)
+
+
+def test_normalize_wide_and_uniformly_controlled():
+    rng = np.random.default_rng(0)
+    # 7-qubit multi-controlled phase: one CMat with six controls, not a 128-entry table
+    d = np.ones(128, dtype=np.complex128)
+    d[-1] = np.exp(0.3j)
+    ops = normalize_instruction(np.diag(d), tuple(range(7)))
+    assert [o.kind for o in ops] == ["mat"] and len(ops[0].controls) == 6
+    np.testing.assert_allclose(_ops_unitary(ops, list(range(7))), np.diag(d), atol=1e-12)
+    # uniformly controlled rotation: different block per control value
+    blocks = []
+    for _ in range(4):
+        a = rng.normal(size=(2, 2)) + 1j * rng.normal(size=(2, 2))
+        q, _r = np.linalg.qr(a)
+        blocks.append(q)
+    u = np.zeros((8, 8), dtype=np.complex128)
+    for x in range(4):
+        u[2 * x : 2 * x + 2, 2 * x : 2 * x + 2] = blocks[x]
+    ops = normalize_instruction(u, (0, 1, 2))
+    np.testing.assert_allclose(_ops_unitary(ops, [0, 1, 2]), u, atol=1e-12)
+    # dense 3-qubit unitary stays one op
+    a = rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8))
+    q, _r = np.linalg.qr(a)
+    ops = normalize_instruction(q, (2, 0, 1))
+    assert len(ops) == 1 and len(ops[0].targets) == 3
+    np.testing.assert_allclose(_ops_unitary(ops, [0, 1, 2]), _embed(q, (2, 0, 1), 3), atol=1e-12)
+
+
+def test_normalize_circuit_fuses_one_qubit_runs():
+    qc = Circuit(3)
+    qc.h(0), qc.t(0), qc.rx(0.3, 0), qc.cx(0, 1), qc.h(1), qc.rxx(0.4, 1, 2), qc.h(2), qc.s(1)
+    ops = normalize_circuit(qc.data)
+    # h,t,rx -> one 1q op; h(1) is folded into rxx, h(2) and s(1) as well
+    assert len(ops) == 3
+    u = ref_sim.circuit_unitary(qc.data, [0, 1, 2])
+    np.testing.assert_allclose(_ops_unitary(ops, [0, 1, 2]), u, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------
+# planner + packed format through the emulator
+# ---------------------------------------------------------------------------------------
+
+
+def test_golden_statevectors_c64(golden_dir):
+    g = load(golden_dir, "statevector.npz")
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        report = []
+        sv, _ = emulate_statevector(qc, report=report)
+        np.testing.assert_allclose(sv, g[case + "_sv"], atol=1e-5, err_msg=case)
+        assert all(w == 1 for _, _, w in report), (case, report)
+
+
+def test_golden_statevectors_c128(golden_dir):
+    g = load(golden_dir, "statevector.npz")
+    for case in ("rand5", "rand10", "ghzqft11"):
+        qc = Circuit.from_arrays(g, case + "_")
+        report = []
+        sv, _ = emulate_statevector(qc, dtype=1, report=report)
+        want = ref_sim.statevector(qc, dtype=np.complex128)
+        np.testing.assert_allclose(sv, want, atol=1e-12, err_msg=case)
+        assert all(w == 1 for _, _, w in report), (case, report)
+
+
+def test_golden_fusion_circuits(golden_dir):
+    g = load(golden_dir, "fusion.npz")
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        sv, _ = emulate_statevector(qc)
+        np.testing.assert_allclose(sv, g[case + "_sv"], atol=1e-5, err_msg=case)
+
+
+@pytest.mark.parametrize("T,r,L", [(9, 4, 4), (10, 3, 4), (11, 4, 5), (12, 4, 4), (13, 5, 4), (12, 5, 6), (13, 4, 4)])
+def test_tile_geometries(T, r, L):
+    qc = random_circuit(13, 4, seed=T * 10 + r, two_qubit="cx")
+    qc.rxx(0.3, 0, 12)
+    qc.mcx([1, 5, 9], 0)
+    qc.swap(2, 11)
+    qc.h(11)
+    report = []
+    sv, steps = emulate_statevector(qc, T=T, r=r, L=L, report=report)
+    want = ref_sim.statevector(qc)
+    np.testing.assert_allclose(sv, want, atol=2e-6)
+    assert all(w == 1 for _, _, w in report), report
+    for s in steps:
+        assert len(s.blob) % 256 == 0
+
+
+def test_three_and_four_qubit_dense_ops_and_big_path():
+    rng = np.random.default_rng(5)
+
+    def haar(k):
+        a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        q, _r = np.linalg.qr(a)
+        return q
+
+    qc = Circuit(11)
+    for q in range(11):
+        qc.h(q)
+    qc.unitary(haar(3), (7, 0, 4))
+    qc.unitary(haar(4), (10, 2, 9, 5))
+    qc.unitary(haar(3), (1, 2, 3))
+    qc.unitary(haar(5), (0, 3, 6, 8, 10))  # wider than the register file: big path
+    qc.cz(0, 1)
+    sv, steps = emulate_statevector(qc)
+    assert any(s.kind == "big" for s in steps)
+    np.testing.assert_allclose(sv, ref_sim.statevector(qc), atol=2e-6)
+    sv5, steps5 = emulate_statevector(qc, T=13, r=5)
+    np.testing.assert_allclose(sv5, ref_sim.statevector(qc), atol=2e-6)
+
+
+def test_qft_needs_few_passes():
+    """The point of the design: a 20-qubit GHZ+QFT (250 gates) is a handful of sweeps."""
+    qc = ghz_qft_circuit(20)
+    steps, pos, N = plan_circuit([i for i in qc.data if i.matrix is not None], 20)
+    assert len(steps) <= 8, len(steps)
+    # the final swaps of the QFT are relabels: the map is reversed, no data moved
+    assert pos == list(range(20))
+
+
+def test_small_window_still_correct():
+    qc = random_circuit(10, 6, seed=11)
+    sv, _ = emulate_statevector(qc, window=7)
+    np.testing.assert_allclose(sv, ref_sim.statevector(qc), atol=2e-6)
+
+
+def test_diag_tables_cover_nonlocal_positions():
+    """Diagonal gates and controls on positions outside the tile (and on rank bits via
+    hi_base) are evaluated from the physical index."""
+    qc = Circuit(14)
+    for q in range(14):
+        qc.h(q)
+    qc.cp(0.7, 0, 13)
+    qc.cz(1, 2)
+    qc.mcp(0.4, [0, 1, 12], 13)
+    qc.cx(0, 13)  # control on the top position, target at the bottom
+    qc.mcx([0, 1, 2], 12)
+    sv, steps = emulate_statevector(qc)
+    np.testing.assert_allclose(sv, ref_sim.statevector(qc), atol=2e-6)
+    # sharded: emulate 2 ranks of 13 local positions each, top qubit (= position 13) is the rank bit
+    from qrisp_b200.normalize import normalize_circuit as nc
+    from qrisp_b200.planner import PlanConfig, Planner
+
+    instrs = [i for i in qc.data if i.matrix is not None][14:]  # after the H layer
+    cfg = PlanConfig(13)
+    pos = [13 - q for q in range(14)]
+    steps, need = Planner(cfg, pos, n_total=14).plan(nc(instrs))
+    assert need is None
+    full = np.full(1 << 14, 2.0**-7, dtype=np.complex64)
+    halves = []
+    for rank in range(2):
+        st = full[rank << 13 : (rank + 1) << 13].copy()
+        for s in steps:
+            st = pass_emulator.run(s.blob, st, hi_base=rank << 13)
+        halves.append(st)
+    got = canonical(np.concatenate(halves), pos, 14)
+    np.testing.assert_allclose(got, ref_sim.statevector(qc), atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------
+# run(): circuit rewriting + outcome pruning (host logic), against the reference's results
+# ---------------------------------------------------------------------------------------
+
+
+def _run_emulated(qc):
+    instrs, n, measurements = preprocess.unitarize(qc)
+    c2 = Circuit(n)
+    c2.data = instrs
+    sv, _ = emulate_statevector(c2)
+    measurements.sort(key=lambda x: -x[1])
+    mes_qubits = [q for q, _ in measurements]
+    p = marginal(sv, mes_qubits, n)
+    outcomes, probs = simulator.prune_outcomes(p)
+    probs = simulator.round_probabilities(probs)
+    res = {}
+    for o, pr in zip(outcomes, probs):
+        if pr == 0:
+            continue
+        key = bin(int(o))[2:].zfill(len(mes_qubits))
+        res[key] = res.get(key, 0.0) + float(pr)
+    return res
+
+
+@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz"])
+def test_run_matches_reference_results(golden_dir, fixture):
+    g = load(golden_dir, fixture)
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        if qc.num_qubits > 16:
+            continue  # the emulator is slow; the GPU test covers the wide cases
+        got = _run_emulated(qc)
+        ref = {str(k): float(p) for k, p in zip(g[case + "_keys"], g[case + "_probs"])}
+        for k in set(got) | set(ref):
+            assert abs(got.get(k, 0.0) - ref.get(k, 0.0)) < 1e-5, (case, k)
+
+
+def test_unitarize_matches_oracle_rewriting(golden_dir):
+    g = load(golden_dir, "run.npz")
+    for case in g["cases"]:
+        qc = Circuit.from_arrays(g, str(case) + "_")
+        a = preprocess.unitarize(qc)
+        b = ref_sim.rewrite_measurements(qc)
+        assert a[1] == b[1] and a[2] == b[2]
+        assert [(i.name, i.qubits) for i in a[0]] == [(i.name, i.qubits) for i in b[0]]
+
+
+# ---------------------------------------------------------------------------------------
+# the C-ABI library
+# ---------------------------------------------------------------------------------------
+
+
+def test_library_exports_every_declared_symbol():
+    import re
+
+    from qrisp_b200 import _lib
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "qrisp_b200.h")).read()
+    declared = set(re.findall(r"\b(qb2_[a-z0-9_]+)\s*\(", header))
+    declared -= {"qb2_run_pass_device"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    lib = _lib.load()  # resolves every symbol, checks the ABI version
+    assert lib.qb2_abi_version() == _lib.QB2_ABI_VERSION
+    assert lib.qb2_sample_chunk_bits(30) == 12 and lib.qb2_sample_chunk_bits(8) == 8
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    from qrisp_b200 import _lib
+    from qrisp_b200.simulator import statevector_sim
+
+    with pytest.raises(_lib.Qb2Error):
+        statevector_sim(ghz_qft_circuit(3))
