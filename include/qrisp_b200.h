@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QB2_ABI_VERSION 2
+#define QB2_ABI_VERSION 3
 
 #define QB2_C64 0
 #define QB2_C128 1
@@ -81,8 +81,9 @@ int qb2_init_basis(void *state, int n, uint64_t basis, int dtype, void *stream);
  * store + load per amplitude).  Controls and diagonal gates may involve ANY position
  * (tile, non-tile or rank bits): they are evaluated from the physical index.
  *
- * `header` is a HOST pointer to (at least) the pass header; `blob_dev` is the whole packed
- * pass on the device (256-byte aligned).  `hi_base` holds the bits of the physical index at
+ * `header` is a HOST pointer to the small section of the pass (header.small_bytes bytes);
+ * `blob_dev` is the whole packed pass on the device (256-byte aligned; only its phase tables
+ * are read there).  `hi_base` holds the bits of the physical index at
  * positions >= n (the rank bits of a sharded state; 0 on one GPU).
  */
 int qb2_run_pass(void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev, int dtype,
@@ -129,19 +130,34 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 /* ---------------------------------------------------------------- packed pass layout
  * All offsets are bytes from the start of the blob; the blob is 256-byte aligned on the
  * device.  The first `small_bytes` bytes (header, phases, ops, coefficients, index arrays)
- * are staged in shared memory by every CTA; phase tables stay in global memory.
+ * travel to the kernel BY VALUE as a launch parameter, i.e. they live in the constant bank and
+ * every descriptor read is a uniform constant load; phase tables stay in global memory.
  */
 #define QB2_PASS_MAGIC 0x32425151u /* "QQB2" */
 #define QB2_MAX_TILE_BITS 13
 #define QB2_MAX_REG_BITS 5
 #define QB2_MAX_SEGS 16
-#define QB2_MAX_SMALL_BYTES 24576
+#define QB2_MAX_SMALL_BYTES 8192
 
 #define QB2_OP_MAT1 1 /* 2x2 on register bit b0 */
 #define QB2_OP_MAT2 2 /* 4x4 on register bits b0 < b1 (matrix index bit 0 <-> b0) */
 #define QB2_OP_MAT3 3 /* 8x8 on register bits 0,1,2 */
 #define QB2_OP_MAT4 4 /* 16x16 on register bits 0..3 */
-#define QB2_OP_DIAG 5 /* amp *= exp(2 pi i * (sum of table entries) / 2**32 (C64) or 2**64 (C128)) */
+/* diagonal ops: amp *= exp(2 pi i * phase / 2**32 (C64) or 2**64 (C128)), phase = a sum of
+ * table entries.  "Thread tables" are indexed by thread / tile / rank bits only (one lookup
+ * per thread); the kinds differ in how the phase depends on the register bits. */
+#define QB2_OP_DIAG 5     /* general: up to 4 tables indexed by thread AND register bits (per amplitude) */
+#define QB2_OP_DIAG_THR 6 /* thread tables only: one phase per thread */
+#define QB2_OP_DIAG_BIT 7 /* thread tables + tables that also depend on register bit b0: two phases per
+                             thread; a bit table holds the b0=1 entries `regoff` entries after the b0=0 ones;
+                             flags&1: the b0=0 phase is exactly 0 and is skipped */
+#define QB2_OP_DIAG_VEC 8 /* depends on register bits only: 2**r host-computed unit complex factors at `data` */
+
+/* qb2_op.flags of a QB2_OP_MAT1: the shape of the 2x2 block (all use the same 4 coefficients) */
+#define QB2_MAT1_GENERAL 0
+#define QB2_MAT1_REAL 1 /* all four entries real (H, RY, X...) */
+#define QB2_MAT1_ANTI 2 /* zero diagonal (X, Y and their phases) */
+#define QB2_MAT1_SWAP 3 /* exactly X: the two amplitudes trade places */
 
 typedef struct qb2_seg { /* tile id bits [src, src+len) go to physical bits [dst, dst+len) */
     uint8_t src, dst, len, rsv;
@@ -193,7 +209,8 @@ typedef struct qb2_op { /* 32 bytes */
     uint8_t b1;
     uint8_t ntab_thr; /* DIAG: tables that depend on thread/tile bits only (come first) */
     uint8_t ntab_reg; /* DIAG: tables that also depend on register bits */
-    uint8_t rsv[3];
+    uint8_t flags;
+    uint8_t rsv[2];
 } qb2_op;
 
 typedef struct qb2_piece { /* ((x >> shift) & ((1 << len) - 1)) << out */

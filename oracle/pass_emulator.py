@@ -36,8 +36,9 @@ def parse(blob):
     P.phases = [struct.unpack_from("<8I", b, phases_off + 32 * i)[:6] for i in range(n_phases)]
     P.ops = []
     for i in range(n_ops):
-        cmask, cval, jmask, data, kind, b0, b1, nthr, nreg = struct.unpack_from("<QQIIBBBBB", b, ops_off + 32 * i)
-        P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, kind=kind, b0=b0, b1=b1, nthr=nthr, nreg=nreg))
+        cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags = struct.unpack_from("<QQIIBBBBBB", b, ops_off + 32 * i)
+        P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, kind=kind, b0=b0, b1=b1, nthr=nthr, nreg=nreg,
+                          flags=flags))
     real_t = np.float32 if dtype == 0 else np.float64
     frac_t = np.uint32 if dtype == 0 else np.uint64
     P.real_t, P.frac_t = real_t, frac_t
@@ -122,23 +123,51 @@ def run(blob, state, hi_base=0, report=None):
             X = np.uint64(hi_base) | xloc
             for o in range(first_op, first_op + nops):
                 op = P.ops[o]
-                if op["kind"] == 5:
-                    tb = P.tabs[op["data"] : op["data"] + op["nthr"] + op["nreg"]]
+                if op["kind"] >= 5:
+                    kind = op["kind"]
+                    tb = P.tabs[op["data"] : op["data"] + op["nthr"] + op["nreg"]] if kind != 8 else []
                     s = np.zeros(nthreads, dtype=P.frac_t)
                     for tdesc in tb[: op["nthr"]]:
                         s = s + P.tables[(np.uint64(tdesc["off"]) + _tab_index(tdesc, X)).astype(np.int64)]
-                    sj = np.repeat(s[:, None], NR, axis=1)
-                    for tdesc in tb[op["nthr"] :]:
-                        base = np.uint64(tdesc["off"]) + _tab_index(tdesc, X)
-                        go = P.a16[tdesc["regoff"] : tdesc["regoff"] + NR].astype(np.uint64)
-                        sj = sj + P.tables[(base[:, None] + go[None, :]).astype(np.int64)]
-                    regs = (regs * _phase(sj, P.dtype)).astype(cdt)
+                    if kind == 6:  # DIAG_THR
+                        regs = (regs * _phase(s, P.dtype)[:, None]).astype(cdt)
+                    elif kind == 7:  # DIAG_BIT
+                        s0, s1 = s.copy(), s.copy()
+                        for tdesc in tb[op["nthr"] :]:
+                            e = (np.uint64(tdesc["off"]) + _tab_index(tdesc, X)).astype(np.int64)
+                            s0 = s0 + P.tables[e]
+                            s1 = s1 + P.tables[e + tdesc["regoff"]]
+                        w0, w1 = _phase(s0, P.dtype), _phase(s1, P.dtype)
+                        new = regs.copy()
+                        for j in range(NR):
+                            if (j >> op["b0"]) & 1:
+                                new[:, j] = (regs[:, j] * w1).astype(cdt)
+                            elif not (op["flags"] & 1):
+                                new[:, j] = (regs[:, j] * w0).astype(cdt)
+                        regs = new
+                    elif kind == 8:  # DIAG_VEC
+                        cv = P.coefs[2 * op["data"] : 2 * op["data"] + 2 * NR].astype(np.float64)
+                        regs = (regs * (cv[0::2] + 1j * cv[1::2])[None, :]).astype(cdt)
+                    else:
+                        sj = np.repeat(s[:, None], NR, axis=1)
+                        for tdesc in tb[op["nthr"] :]:
+                            base = np.uint64(tdesc["off"]) + _tab_index(tdesc, X)
+                            go = P.a16[tdesc["regoff"] : tdesc["regoff"] + NR].astype(np.uint64)
+                            sj = sj + P.tables[(base[:, None] + go[None, :]).astype(np.int64)]
+                        regs = (regs * _phase(sj, P.dtype)).astype(cdt)
                 else:
                     k = op["kind"]
                     D = 1 << k
                     bits = [op["b0"], op["b1"]][:k] if k <= 2 else list(range(k))
                     m = P.coefs[2 * op["data"] : 2 * op["data"] + 2 * D * D].astype(np.float64)
                     m = (m[0::2] + 1j * m[1::2]).reshape(D, D)
+                    if k == 1:  # the specialised 2x2 paths read only part of the coefficients
+                        if op["flags"] == 1:
+                            m = m.real.astype(np.complex128)
+                        elif op["flags"] == 2:
+                            m = np.array([[0, m[0, 1]], [m[1, 0], 0]])
+                        elif op["flags"] == 3:
+                            m = np.array([[0, 1], [1, 0]], dtype=np.complex128)
                     on = ((X ^ np.uint64(op["cval"])) & np.uint64(op["cmask"])) == 0
                     tmask = sum(1 << bb for bb in bits)
                     new = regs.copy()

@@ -13,6 +13,7 @@
 // the host so that both the store and the load side are bank-conflict free.
 //
 // HBM-bound by construction: algorithmic bytes per launch = 2 * 2**n * sizeof(amplitude).
+#include <cstring>
 #include <type_traits>
 
 #include "qb2_internal.cuh"
@@ -133,23 +134,72 @@ __device__ __forceinline__ void st_stream(V *p, const V v) {
     __stcs(p, v);
 }
 
+struct PassParams {  // the small section of a pass, passed by value: lives in the constant bank
+    uint4 q[QB2_MAX_SMALL_BYTES / 16];
+};
+
+template <typename real, int RB, int B>
+__device__ __forceinline__ void mat1_real(real (&re)[1 << RB], real (&im)[1 << RB], const real a, const real b,
+                                          const real c, const real d, const uint32_t jmask) {
+    static_for<0, (1 << RB) / 2>([&](auto G) {
+        constexpr int g = decltype(G)::value;
+        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        constexpr int j1 = j0 | (1 << B);
+        if ((jmask >> j0) & 1u) {
+            const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
+            re[j0] = fma(a, x0r, b * x1r);
+            im[j0] = fma(a, x0i, b * x1i);
+            re[j1] = fma(c, x0r, d * x1r);
+            im[j1] = fma(c, x0i, d * x1i);
+        }
+    });
+}
+
+// anti-diagonal 2x2: new0 = p * x1, new1 = q * x0
+template <typename real, int RB, int B>
+__device__ __forceinline__ void mat1_anti(real (&re)[1 << RB], real (&im)[1 << RB], const real pr, const real pi,
+                                          const real qr, const real qi, const uint32_t jmask) {
+    static_for<0, (1 << RB) / 2>([&](auto G) {
+        constexpr int g = decltype(G)::value;
+        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        constexpr int j1 = j0 | (1 << B);
+        if ((jmask >> j0) & 1u) {
+            const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
+            re[j0] = fma(pr, x1r, -pi * x1i);
+            im[j0] = fma(pr, x1i, pi * x1r);
+            re[j1] = fma(qr, x0r, -qi * x0i);
+            im[j1] = fma(qr, x0i, qi * x0r);
+        }
+    });
+}
+
+template <typename real, int RB, int B>
+__device__ __forceinline__ void mat1_swap(real (&re)[1 << RB], real (&im)[1 << RB], const uint32_t jmask) {
+    static_for<0, (1 << RB) / 2>([&](auto G) {
+        constexpr int g = decltype(G)::value;
+        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        constexpr int j1 = j0 | (1 << B);
+        if ((jmask >> j0) & 1u) {
+            const real tr = re[j0], ti = im[j0];
+            re[j0] = re[j1];
+            im[j0] = im[j1];
+            re[j1] = tr;
+            im[j1] = ti;
+        }
+    });
+}
+
 template <typename real, int RB, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
-    pass_kernel(typename Traits<real>::vec *__restrict__ state, const uint8_t *__restrict__ blob,
-                const uint64_t hi_base, const uint32_t ntiles, const uint32_t small_bytes, const uint32_t roots_off,
-                const uint32_t tile_off) {
+    pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
+                const uint64_t hi_base, const uint32_t ntiles, const uint32_t roots_off, const uint32_t tile_off,
+                const __grid_constant__ PassParams P) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
     constexpr int NR = 1 << RB;
     extern __shared__ __align__(16) uint8_t smem[];
 
     const uint32_t tid = threadIdx.x;
-    // ---- stage the small section (header, phases, ops, coefficients, index arrays)
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(blob);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        for (uint32_t i = tid; i < small_bytes / 16; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
     vec *const roots = reinterpret_cast<vec *>(smem + roots_off);
     if constexpr (std::is_same<real, float>::value) {
         for (uint32_t i = tid; i < NROOT; i += blockDim.x) {
@@ -157,17 +207,18 @@ __global__ void __launch_bounds__(MAXT, MINB)
             sincospif((float)i * (2.0f / NROOT), &s, &c);
             roots[i] = make_float2(c, s);
         }
+        __syncthreads();
     }
-    __syncthreads();
 
-    const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(smem);
-    const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(smem + H->phases_off);
-    const qb2_op *const ops = reinterpret_cast<const qb2_op *>(smem + H->ops_off);
-    const real *const coefs = reinterpret_cast<const real *>(smem + H->coef_off);
-    const uint16_t *const a16 = reinterpret_cast<const uint16_t *>(smem + H->u16_off);
-    const uint64_t *const a64 = reinterpret_cast<const uint64_t *>(smem + H->u64_off);
-    const qb2_tab *const tabs = reinterpret_cast<const qb2_tab *>(smem + H->tabdesc_off);
-    const frac *const tables = reinterpret_cast<const frac *>(blob + H->tab_off);
+    // every descriptor read below is a constant-bank load with a warp-uniform offset
+    const uint8_t *const pb = reinterpret_cast<const uint8_t *>(&P);
+    const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(pb);
+    const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(pb + H->phases_off);
+    const qb2_op *const ops = reinterpret_cast<const qb2_op *>(pb + H->ops_off);
+    const real *const coefs = reinterpret_cast<const real *>(pb + H->coef_off);
+    const uint16_t *const a16 = reinterpret_cast<const uint16_t *>(pb + H->u16_off);
+    const uint64_t *const a64 = reinterpret_cast<const uint64_t *>(pb + H->u64_off);
+    const qb2_tab *const tabs = reinterpret_cast<const qb2_tab *>(pb + H->tabdesc_off);
     vec *const tile = reinterpret_cast<vec *>(smem + tile_off);
     const int TB = (int)H->T - RB;  // thread bits
     const uint32_t n_phases = H->n_phases;
@@ -237,16 +288,18 @@ __global__ void __launch_bounds__(MAXT, MINB)
             }
             const uint64_t X = hi_base | xloc;
             // ---- ops of this phase, on registers
-            for (uint32_t o = ph.first_op; o < ph.first_op + ph.n_ops; ++o) {
+            const uint32_t op_end = ph.first_op + ph.n_ops;
+            for (uint32_t o = ph.first_op; o < op_end; ++o) {
                 const qb2_op &op = ops[o];
                 const uint32_t kind = op.kind;
-                if (kind == QB2_OP_DIAG) {
+                if (kind >= QB2_OP_DIAG) {
                     const qb2_tab *tb = tabs + op.data;
                     frac sum = 0;
                     const int nthr = op.ntab_thr;
                     for (int i = 0; i < nthr; ++i) sum += __ldg(tables + tb[i].off + tab_index(tb[i], X));
+                    tb += nthr;
                     const int nreg = op.ntab_reg;
-                    if (nreg == 0) {
+                    if (kind == QB2_OP_DIAG_THR) {
                         const vec w = unit_phase(sum, roots);
                         static_for<0, NR>([&](auto J) {
                             constexpr int j = decltype(J)::value;
@@ -254,9 +307,49 @@ __global__ void __launch_bounds__(MAXT, MINB)
                             re[j] = fma(xr_, w.x, -xi_ * w.y);
                             im[j] = fma(xr_, w.y, xi_ * w.x);
                         });
-                    } else {
-                        tb += nthr;
-                        const frac *t0 = nullptr, *t1 = nullptr, *t2 = nullptr, *t3 = nullptr;
+                    } else if (kind == QB2_OP_DIAG_BIT) {
+                        // phase depends on the thread and on ONE register bit: two phases per thread
+                        frac s0 = sum, s1 = sum;
+                        for (int i = 0; i < nreg; ++i) {
+                            const frac *e = tables + tb[i].off + tab_index(tb[i], X);
+                            s0 += __ldg(e);
+                            s1 += __ldg(e + tb[i].regoff);
+                        }
+                        const vec w0 = unit_phase(s0, roots);
+                        const vec w1 = unit_phase(s1, roots);
+                        const bool skip0 = (op.flags & 1u) != 0;
+                        const int b0 = op.b0;
+                        static_for<0, RB>([&](auto B) {
+                            constexpr int bb = decltype(B)::value;
+                            if (b0 == bb) {
+                                static_for<0, NR>([&](auto J) {
+                                    constexpr int j = decltype(J)::value;
+                                    if constexpr ((j >> bb) & 1) {
+                                        const real xr_ = re[j], xi_ = im[j];
+                                        re[j] = fma(xr_, w1.x, -xi_ * w1.y);
+                                        im[j] = fma(xr_, w1.y, xi_ * w1.x);
+                                    } else {
+                                        if (!skip0) {
+                                            const real xr_ = re[j], xi_ = im[j];
+                                            re[j] = fma(xr_, w0.x, -xi_ * w0.y);
+                                            im[j] = fma(xr_, w0.y, xi_ * w0.x);
+                                        }
+                                    }
+                                });
+                            }
+                        });
+                    } else if (kind == QB2_OP_DIAG_VEC) {
+                        // phases that depend on register bits only: host-computed, uniform
+                        const real *cv = coefs + 2 * (size_t)op.data;
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            const real wr = cv[2 * j], wi = cv[2 * j + 1];
+                            const real xr_ = re[j], xi_ = im[j];
+                            re[j] = fma(xr_, wr, -xi_ * wi);
+                            im[j] = fma(xr_, wi, xi_ * wr);
+                        });
+                    } else {  // QB2_OP_DIAG: general, one table sum per amplitude
+                        const frac *t0 = tables, *t1 = tables, *t2 = tables, *t3 = tables;
                         const uint16_t *g0 = a16, *g1 = a16, *g2 = a16, *g3 = a16;
                         t0 = tables + tb[0].off + tab_index(tb[0], X);
                         g0 = a16 + tb[0].regoff;
@@ -289,9 +382,29 @@ __global__ void __launch_bounds__(MAXT, MINB)
                     const uint32_t jmask = op.jmask;
                     const int b0 = op.b0, b1 = op.b1;
                     if (kind == QB2_OP_MAT1) {
-                        static_for<0, RB>([&](auto B) {
-                            if (b0 == decltype(B)::value) apply_mat<real, RB, 1, decltype(B)::value>(re, im, m, jmask);
-                        });
+                        const uint32_t shape = op.flags;
+                        if (shape == QB2_MAT1_SWAP) {
+                            static_for<0, RB>([&](auto B) {
+                                if (b0 == decltype(B)::value) mat1_swap<real, RB, decltype(B)::value>(re, im, jmask);
+                            });
+                        } else if (shape == QB2_MAT1_REAL) {
+                            const real a = m[0], b = m[2], c = m[4], d = m[6];
+                            static_for<0, RB>([&](auto B) {
+                                if (b0 == decltype(B)::value)
+                                    mat1_real<real, RB, decltype(B)::value>(re, im, a, b, c, d, jmask);
+                            });
+                        } else if (shape == QB2_MAT1_ANTI) {
+                            const real pr = m[2], pi = m[3], qr = m[4], qi = m[5];
+                            static_for<0, RB>([&](auto B) {
+                                if (b0 == decltype(B)::value)
+                                    mat1_anti<real, RB, decltype(B)::value>(re, im, pr, pi, qr, qi, jmask);
+                            });
+                        } else {
+                            static_for<0, RB>([&](auto B) {
+                                if (b0 == decltype(B)::value)
+                                    apply_mat<real, RB, 1, decltype(B)::value>(re, im, m, jmask);
+                            });
+                        }
                     } else if (kind == QB2_OP_MAT2) {
                         static_for<0, RB>([&](auto B0) {
                             static_for<decltype(B0)::value + 1, RB>([&](auto B1) {
@@ -344,12 +457,13 @@ template <typename real, int RB, int MAXT, int MINB>
 int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
                    cudaStream_t s) {
     using vec = typename Traits<real>::vec;
+    using frac = typename Traits<real>::frac;
     auto kern = pass_kernel<real, RB, MAXT, MINB>;
     static bool attr_set = false;
     static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
     const uint32_t threads = 1u << (h->T - RB);
-    const uint32_t roots_off = (h->small_bytes + 15u) & ~15u;
-    const uint32_t tile_off = roots_off + (std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0);
+    const uint32_t roots_off = 0;
+    const uint32_t tile_off = std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0;
     const size_t tile_bytes = h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0;
     const size_t smem = tile_off + tile_bytes;
     if (!attr_set) {
@@ -367,8 +481,11 @@ int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, cons
     }
     uint32_t grid = (uint32_t)(occ_cache * sm_count());
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), reinterpret_cast<const uint8_t *>(blob_dev), hi_base,
-                                     ntiles, h->small_bytes, roots_off, tile_off);
+    // the small section travels as a kernel parameter (constant bank); the tables stay in HBM
+    static PassParams params;
+    memcpy(&params, h, h->small_bytes);
+    const frac *tables = reinterpret_cast<const frac *>(reinterpret_cast<const uint8_t *>(blob_dev) + h->tab_off);
+    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, hi_base, ntiles, roots_off, tile_off, params);
     count_launch();
     return check_cuda(cudaGetLastError(), "pass_kernel launch");
 }

@@ -219,7 +219,12 @@ class Program:
             self._host = host
             sv.io["h2d"] += total
         for s in steps:
-            self._headers.append(ctypes.create_string_buffer(s.blob[:128], 128) if s.kind == "pass" else None)
+            # the small section (header.small_bytes) is handed to the launch by value
+            if s.kind == "pass":
+                small = int.from_bytes(s.blob[8:12], "little")
+                self._headers.append(ctypes.create_string_buffer(s.blob[:small], small))
+            else:
+                self._headers.append(None)
         self.n_passes = sum(1 for s in steps if s.kind == "pass")
         self.n_kernel_ops = sum(s.n_ops for s in steps if s.kind == "pass")
         self.n_gate_ops = sum(s.n_gate_ops for s in steps if s.kind == "pass") + sum(1 for s in steps if s.kind != "pass")

@@ -31,9 +31,10 @@ from .normalize import CMat, DiagTerm, Relabel
 QB2_PASS_MAGIC = 0x32425151
 QB2_C64, QB2_C128 = 0, 1
 OP_MAT = {1: 1, 2: 2, 3: 3, 4: 4}
-OP_DIAG = 5
+OP_DIAG, OP_DIAG_THR, OP_DIAG_BIT, OP_DIAG_VEC = 5, 6, 7, 8
+MAT1_GENERAL, MAT1_REAL, MAT1_ANTI, MAT1_SWAP = 0, 1, 2, 3
 MAX_SEGS = 16
-MAX_SMALL_BYTES = 24576
+MAX_SMALL_BYTES = 8192
 MAX_TAB_BITS = 10
 MAX_PIECES = 6
 MAX_REG_TABS = 4
@@ -335,24 +336,35 @@ class Planner:
                         terms.append(pops[i])
                         i += 1
                     n_gate_ops += len(terms)
-                    for thr_tabs, reg_tabs in _build_tables(terms, R, cfg):
+                    for dop in _build_diag_ops(terms, R, cfg):
                         first_tab = len(tabdescs)
-                        for positions, vals in thr_tabs + reg_tabs:
+                        data = first_tab
+                        if dop["kind"] == OP_DIAG_VEC:
+                            data = len(coefs)
+                            coefs.extend(np.exp(2j * np.pi * dop["vec"]))
+                        for positions, vals in dop["thr"]:
+                            tabdescs.append((_pieces(positions), n_tab_entries, 0))
+                            tables.append(_to_frac(vals, frac_t))
+                            n_tab_entries += len(vals)
+                        for positions, vals in dop["reg"]:
                             thr_positions = [x for x in positions if x not in R]
                             reg_positions = [x for x in positions if x in R]
-                            pieces = _pieces(thr_positions)
                             nthr = len(thr_positions)
-                            regoff = 0
-                            if reg_positions:
+                            if dop["kind"] == OP_DIAG_BIT:
+                                regoff = 1 << nthr  # the b0=1 half follows the b0=0 half
+                            else:
                                 regoff = add16(
                                     sum(((j >> R.index(x)) & 1) << (nthr + k) for k, x in enumerate(reg_positions))
                                     for j in range(NR)
                                 )
-                            tabdescs.append((pieces, n_tab_entries, regoff))
+                            tabdescs.append((_pieces(thr_positions), n_tab_entries, regoff))
                             tables.append(_to_frac(vals, frac_t))
                             n_tab_entries += len(vals)
                         ops_b.append(
-                            struct.pack("<QQIIBBBBB3x", 0, 0, 0, first_tab, OP_DIAG, 0, 0, len(thr_tabs), len(reg_tabs))
+                            struct.pack(
+                                "<QQIIBBBBBB2x", 0, 0, 0, data, dop["kind"], dop.get("b0", 0), 0, len(dop["thr"]),
+                                len(dop["reg"]), dop.get("flags", 0),
+                            )
                         )
                         op_count += 1
                     continue
@@ -379,7 +391,8 @@ class Planner:
                 coefs.extend(m.reshape(-1))
                 ops_b.append(
                     struct.pack(
-                        "<QQIIBBBBB3x", cmask, cval, jmask, data, OP_MAT[k], sbits[0], sbits[1] if k > 1 else 0, 0, 0
+                        "<QQIIBBBBBB2x", cmask, cval, jmask, data, OP_MAT[k], sbits[0], sbits[1] if k > 1 else 0, 0, 0,
+                        _mat1_shape(m) if k == 1 else 0,
                     )
                 )
                 op_count += 1
@@ -586,61 +599,118 @@ def _to_frac(turns, frac_t):
     return (hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)
 
 
-def _build_tables(terms, R, cfg):
-    """Merge diagonal terms into phase tables.
+def _mat1_shape(m):
+    """Which specialised 2x2 kernel path applies (include/qrisp_b200.h QB2_MAT1_*)."""
+    tiny = 1e-16
+    if abs(m[0, 0]) < tiny and abs(m[1, 1]) < tiny:
+        if abs(m[0, 1] - 1) < tiny and abs(m[1, 0] - 1) < tiny:
+            return MAT1_SWAP
+        return MAT1_ANTI
+    if np.max(np.abs(m.imag)) < tiny:
+        return MAT1_REAL
+    return MAT1_GENERAL
 
-    Yields ``(thread_tables, register_tables)`` groups, one per DIAG op; every table is
-    ``(sorted positions, turns)`` with the thread/tile positions as the low index bits
-    (ascending, so that neighbouring lanes read neighbouring entries) and the register
-    positions as the high index bits.
-    """
-    Rset = set(R)
-    tabs = []  # [positions(set), list of terms]
-    for _, positions, turns in terms:
+
+def _merge_tables(terms, Rset, max_bits):
+    """Greedy merge of diagonal terms into tables.  Returns [(positions, [terms])] where
+    ``positions`` is the union of the terms' positions (a set)."""
+    tabs = []
+    for positions, turns in terms:
         pset = set(positions)
-        placed = False
-        has_reg = bool(pset & Rset)
         for tab in tabs:
-            if bool(tab[0] & Rset) != has_reg and len(tab[0] | pset) > len(tab[0]):
-                # do not turn a cheap per-thread table into a per-amplitude one
-                continue
             u = tab[0] | pset
-            if len(u) <= MAX_TAB_BITS and _n_runs(sorted(x for x in u if x not in Rset)) <= MAX_PIECES:
+            if len(u) <= max_bits and _n_runs(sorted(x for x in u if x not in Rset)) <= MAX_PIECES:
                 tab[0] = u
                 tab[1].append((positions, turns))
-                placed = True
                 break
-        if not placed:
-            if len(pset) > MAX_TAB_BITS + 2 or _n_runs(sorted(x for x in pset if x not in Rset)) > MAX_PIECES:
+        else:
+            if len(pset) > max_bits or _n_runs(sorted(x for x in pset if x not in Rset)) > MAX_PIECES:
                 raise RuntimeError("diagonal term too wide for a phase table")
             tabs.append([pset, [(positions, turns)]])
-    built = []
-    for pset, tterms in tabs:
-        thr = sorted(x for x in pset if x not in Rset)
-        reg = sorted((x for x in pset if x in Rset), key=R.index)
-        order = thr + reg
-        nb = len(order)
-        idx = np.arange(1 << nb)
-        vals = np.zeros(1 << nb, dtype=np.float64)
-        for positions, turns in tterms:
-            sub = np.zeros(1 << nb, dtype=np.int64)
+    return tabs
+
+
+def _table_values(order, tterms):
+    """Sum of the terms over the index space whose bit b is position ``order[b]``."""
+    nb = len(order)
+    idx = np.arange(1 << nb)
+    vals = np.zeros(1 << nb, dtype=np.float64)
+    for positions, turns in tterms:
+        sub = np.zeros(1 << nb, dtype=np.int64)
+        for b, x in enumerate(positions):
+            sub |= ((idx >> order.index(x)) & 1) << b
+        vals += turns[sub]
+    return vals
+
+
+def _build_diag_ops(terms, R, cfg):
+    """Turn a run of (commuting) diagonal terms into DIAG ops.
+
+    The terms are split by how their phase depends on the register bits of the phase,
+    because that decides how much work a thread has to do per amplitude:
+
+    * no register bit       -> thread table (one lookup per thread);
+    * register bits only    -> one host-computed vector of unit factors (DIAG_VEC);
+    * exactly one register bit (+ thread bits) -> DIAG_BIT: two phases per thread;
+    * anything else         -> general DIAG: a table sum per amplitude.
+
+    Every table is ``(positions, turns)``: thread/tile positions ascending as the low index
+    bits (neighbouring lanes read neighbouring entries), register positions above them.
+    """
+    Rset = set(R)
+    NR = 1 << len(R)
+    vec = np.zeros(NR, dtype=np.float64)
+    have_vec = False
+    thr_terms, gen_terms = [], []
+    bit_terms = {}
+    for _, positions, turns in terms:
+        regp = [x for x in positions if x in Rset]
+        if len(regp) == len(positions):
+            j = np.arange(NR)
+            sub = np.zeros(NR, dtype=np.int64)
             for b, x in enumerate(positions):
-                sub |= ((idx >> order.index(x)) & 1) << b
-            vals += turns[sub]
-        built.append((order, vals, bool(reg)))
-    thr_tabs = [(o, v) for o, v, has in built if not has]
-    reg_tabs = [(o, v) for o, v, has in built if has]
-    groups = []
-    if not reg_tabs:
-        groups.append((thr_tabs, []))
-    else:
-        for s in range(0, len(reg_tabs), MAX_REG_TABS):
-            groups.append((thr_tabs if s == 0 else [], reg_tabs[s : s + MAX_REG_TABS]))
-    # the op encodes the table counts in one byte each
-    out = []
-    for tt, rt in groups:
-        while len(tt) > 200:
-            out.append((tt[:200], []))
-            tt = tt[200:]
-        out.append((tt, rt))
-    return out
+                sub |= ((j >> R.index(x)) & 1) << b
+            vec += turns[sub]
+            have_vec = True
+        elif not regp:
+            thr_terms.append((positions, turns))
+        elif len(regp) == 1:
+            bit_terms.setdefault(R.index(regp[0]), []).append((positions, turns))
+        else:
+            gen_terms.append((positions, turns))
+
+    thr_tabs = []
+    for pset, tterms in _merge_tables(thr_terms, Rset, MAX_TAB_BITS):
+        order = sorted(pset)
+        thr_tabs.append((order, _table_values(order, tterms)))
+
+    ops = []
+    if have_vec and np.any(np.abs(vec - np.rint(vec)) > 0):
+        ops.append({"kind": OP_DIAG_VEC, "vec": vec, "thr": [], "reg": []})
+    for b in sorted(bit_terms):
+        reg_tabs = []
+        for pset, tterms in _merge_tables(bit_terms[b], Rset, MAX_TAB_BITS):
+            order = sorted(x for x in pset if x not in Rset) + [R[b]]
+            reg_tabs.append((order, _table_values(order, tterms)))
+        for s in range(0, len(reg_tabs), 200):
+            ops.append({"kind": OP_DIAG_BIT, "b0": b, "thr": [], "reg": reg_tabs[s : s + 200]})
+    gen_tabs = []
+    for pset, tterms in _merge_tables(gen_terms, Rset, MAX_TAB_BITS):
+        order = sorted(x for x in pset if x not in Rset) + sorted((x for x in pset if x in Rset), key=R.index)
+        gen_tabs.append((order, _table_values(order, tterms)))
+    for s in range(0, len(gen_tabs), MAX_REG_TABS):
+        ops.append({"kind": OP_DIAG, "thr": [], "reg": gen_tabs[s : s + MAX_REG_TABS]})
+    # the thread tables ride on the first op that evaluates tables anyway
+    while thr_tabs:
+        chunk, thr_tabs = thr_tabs[:200], thr_tabs[200:]
+        host = next((o for o in ops if o["kind"] in (OP_DIAG_BIT, OP_DIAG) and not o["thr"]), None)
+        if host is None:
+            ops.append({"kind": OP_DIAG_THR, "thr": chunk, "reg": []})
+        else:
+            host["thr"] = chunk
+    for o in ops:
+        if o["kind"] == OP_DIAG_BIT and not o["thr"]:
+            frac_t = np.uint32 if cfg.dtype == QB2_C64 else np.uint64
+            if all(not np.any(_to_frac(v[: len(v) // 2], frac_t)) for _, v in o["reg"]):
+                o["flags"] = 1  # the b0=0 phase is exactly zero: skip those amplitudes
+    return ops
