@@ -218,10 +218,27 @@ typedef struct qb2_piece { /* ((x >> shift) & ((1 << len) - 1)) << out */
 } qb2_piece;
 
 typedef struct qb2_tab { /* 32 bytes */
-    qb2_piece p[6];  /* pieces of the physical index of the thread's register 0 */
+    qb2_piece p[6];  /* pieces of the physical index of the thread's register 0;
+                        p[0].rsv = number of pieces used, p[1].rsv != 0: this slot is a qb2_mul */
     uint32_t off;    /* first entry of the table (entries, from tab_off) */
-    uint32_t regoff; /* index into the u16 area: uint16[2**r] index offset of register j */
+    uint32_t regoff; /* DIAG: index into the u16 area, uint16[2**r] index offset of register j;
+                        DIAG_BIT: distance (entries) from the b0=0 entry to the b0=1 entry */
 } qb2_tab;
+
+/* The multiplier form of a table slot (same 32 bytes): phase = mult * v, v = (x >> shift) & mask,
+ * modulo one turn.  As a DIAG_BIT table it applies to the b0=1 half only. */
+typedef struct qb2_mul {
+    uint8_t rsv0[3];
+    uint8_t zero;   /* = qb2_tab.p[0].rsv: 0 pieces */
+    uint8_t shift;
+    uint8_t brev;   /* non-zero: v = bitreverse32(v) >> rsh before the multiplication */
+    uint8_t rsh;
+    uint8_t is_mul; /* = qb2_tab.p[1].rsv: non-zero */
+    uint32_t mask;
+    uint32_t rsv2;
+    uint64_t mult;  /* turn fraction per unit of the masked index (low 32 bits used for C64) */
+    uint64_t rsv3;
+} qb2_mul;
 
 #ifdef __cplusplus
 }

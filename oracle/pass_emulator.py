@@ -48,7 +48,11 @@ def parse(blob):
     P.tabs = []
     for i in range(ntd):
         raw = struct.unpack_from("<24BII", b, tabdesc_off + 32 * i)
-        pieces = [(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2]) for k in range(6)]
+        if raw[7]:  # qb2_mul
+            _z, shift, brev, rsh, is_mul, mask, _r, mult, _r3 = struct.unpack_from("<3xBBBBBIIQQ", b, tabdesc_off + 32 * i)
+            P.tabs.append(dict(mul=(shift, mask, mult, brev, rsh)))
+            continue
+        pieces = [(raw[4 * k], raw[4 * k + 1], raw[4 * k + 2]) for k in range(raw[3])]
         P.tabs.append(dict(pieces=pieces, off=raw[24], regoff=raw[25]))
     P.a16 = np.frombuffer(b, dtype=np.uint16, count=(small - u16_off) // 2, offset=u16_off)
     P.tables = np.frombuffer(b, dtype=frac_t, count=(total - tab_off) // np.dtype(frac_t).itemsize, offset=tab_off)
@@ -61,6 +65,20 @@ def _tab_index(tab, X):
         if ln:
             idx |= ((X >> np.uint64(shift)) & np.uint64((1 << ln) - 1)) << np.uint64(out)
     return idx
+
+
+def _mul_phase(tdesc, X, frac_t):
+    shift, mask, mult, brev, rsh = tdesc["mul"]
+    v = ((X >> np.uint64(shift)) & np.uint64(mask)).astype(np.uint64)
+    if brev:
+        rv = np.zeros_like(v)
+        for bit in range(32):
+            rv |= ((v >> np.uint64(bit)) & np.uint64(1)) << np.uint64(31 - bit)
+        v = rv >> np.uint64(rsh)
+    bits = 32 if frac_t == np.uint32 else 64
+    with np.errstate(over="ignore"):
+        prod = v * np.uint64(mult % (1 << 64))  # wraps modulo 2**64
+    return (prod & np.uint64((1 << bits) - 1)).astype(frac_t)
 
 
 def _phase(turns, dtype):
@@ -128,12 +146,18 @@ def run(blob, state, hi_base=0, report=None):
                     tb = P.tabs[op["data"] : op["data"] + op["nthr"] + op["nreg"]] if kind != 8 else []
                     s = np.zeros(nthreads, dtype=P.frac_t)
                     for tdesc in tb[: op["nthr"]]:
-                        s = s + P.tables[(np.uint64(tdesc["off"]) + _tab_index(tdesc, X)).astype(np.int64)]
+                        if "mul" in tdesc:
+                            s = s + _mul_phase(tdesc, X, P.frac_t)
+                        else:
+                            s = s + P.tables[(np.uint64(tdesc["off"]) + _tab_index(tdesc, X)).astype(np.int64)]
                     if kind == 6:  # DIAG_THR
                         regs = (regs * _phase(s, P.dtype)[:, None]).astype(cdt)
                     elif kind == 7:  # DIAG_BIT
                         s0, s1 = s.copy(), s.copy()
                         for tdesc in tb[op["nthr"] :]:
+                            if "mul" in tdesc:
+                                s1 = s1 + _mul_phase(tdesc, X, P.frac_t)
+                                continue
                             e = (np.uint64(tdesc["off"]) + _tab_index(tdesc, X)).astype(np.int64)
                             s0 = s0 + P.tables[e]
                             s1 = s1 + P.tables[e + tdesc["regoff"]]

@@ -116,13 +116,25 @@ __device__ __forceinline__ double2 unit_phase(const uint64_t turns, const double
 }
 
 __device__ __forceinline__ uint32_t tab_index(const qb2_tab &t, const uint64_t x) {
+    const int np = t.p[0].rsv;  // number of pieces
     uint32_t idx = 0;
-#pragma unroll
-    for (int p = 0; p < 6; ++p) {
+    for (int p = 0; p < np; ++p) {
         const qb2_piece pc = t.p[p];
-        if (pc.len != 0) idx |= ((uint32_t)(x >> pc.shift) & ((1u << pc.len) - 1u)) << pc.out;
+        idx |= ((uint32_t)(x >> pc.shift) & ((1u << pc.len) - 1u)) << pc.out;
     }
     return idx;
+}
+
+// A table whose entries are a multiple of the index needs no memory: the phase of a ladder of
+// controlled phases with geometric angles (QFT, QPE, Fourier arithmetic) is
+// mult * (bits of the physical index) mod 1 turn.
+__device__ __forceinline__ bool tab_is_mul(const qb2_tab &t) { return t.p[1].rsv != 0; }
+template <typename frac>
+__device__ __forceinline__ frac tab_mul(const qb2_tab &t, const uint64_t x) {
+    const qb2_mul &m = reinterpret_cast<const qb2_mul &>(t);
+    uint32_t v = (uint32_t)(x >> m.shift) & m.mask;
+    if (m.brev) v = __brev(v) >> m.rsh;  // angles that halve with increasing position
+    return (frac)m.mult * (frac)v;
 }
 
 template <typename V>
@@ -296,7 +308,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
                     const qb2_tab *tb = tabs + op.data;
                     frac sum = 0;
                     const int nthr = op.ntab_thr;
-                    for (int i = 0; i < nthr; ++i) sum += __ldg(tables + tb[i].off + tab_index(tb[i], X));
+                    for (int i = 0; i < nthr; ++i)
+                        sum += tab_is_mul(tb[i]) ? tab_mul<frac>(tb[i], X)
+                                                 : __ldg(tables + tb[i].off + tab_index(tb[i], X));
                     tb += nthr;
                     const int nreg = op.ntab_reg;
                     if (kind == QB2_OP_DIAG_THR) {
@@ -311,13 +325,20 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         // phase depends on the thread and on ONE register bit: two phases per thread
                         frac s0 = sum, s1 = sum;
                         for (int i = 0; i < nreg; ++i) {
-                            const frac *e = tables + tb[i].off + tab_index(tb[i], X);
-                            s0 += __ldg(e);
-                            s1 += __ldg(e + tb[i].regoff);
+                            if (tab_is_mul(tb[i])) {  // b0 * (mult * index bits): nothing for b0 = 0
+                                s1 += tab_mul<frac>(tb[i], X);
+                            } else {
+                                const frac *e = tables + tb[i].off + tab_index(tb[i], X);
+                                s0 += __ldg(e);
+                                s1 += __ldg(e + tb[i].regoff);
+                            }
                         }
-                        const vec w0 = unit_phase(s0, roots);
-                        const vec w1 = unit_phase(s1, roots);
                         const bool skip0 = (op.flags & 1u) != 0;
+                        vec w0;
+                        w0.x = 1;
+                        w0.y = 0;
+                        if (!skip0) w0 = unit_phase(s0, roots);
+                        const vec w1 = unit_phase(s1, roots);
                         const int b0 = op.b0;
                         static_for<0, RB>([&](auto B) {
                             constexpr int bb = decltype(B)::value;

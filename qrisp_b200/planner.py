@@ -22,6 +22,7 @@ Everything here is host logic on small arrays; nothing touches amplitudes.
 
 from __future__ import annotations
 
+import os
 import struct
 
 import numpy as np
@@ -46,6 +47,11 @@ class PlanConfig:
 
     def __init__(self, n, dtype=QB2_C64, T=None, r=None, L=4):
         self.dtype = dtype
+        # tuning knobs (bench sweeps): QB2_REG_BITS / QB2_TILE_BITS override the defaults
+        if r is None and os.environ.get("QB2_REG_BITS"):
+            r = int(os.environ["QB2_REG_BITS"])
+        if T is None and os.environ.get("QB2_TILE_BITS"):
+            T = int(os.environ["QB2_TILE_BITS"])
         if r is None:
             r = 4 if dtype == QB2_C64 else 3
         if T is None:
@@ -342,17 +348,18 @@ class Planner:
                         if dop["kind"] == OP_DIAG_VEC:
                             data = len(coefs)
                             coefs.extend(np.exp(2j * np.pi * dop["vec"]))
-                        for positions, vals in dop["thr"]:
-                            tabdescs.append((_pieces(positions), n_tab_entries, 0))
-                            tables.append(_to_frac(vals, frac_t))
-                            n_tab_entries += len(vals)
-                        for positions, vals in dop["reg"]:
+                        for tab in dop["thr"] + dop["reg"]:
+                            if tab[0] == "mul":
+                                tabdescs.append(tab)
+                                continue
+                            _, positions, vals = tab
                             thr_positions = [x for x in positions if x not in R]
                             reg_positions = [x for x in positions if x in R]
                             nthr = len(thr_positions)
-                            if dop["kind"] == OP_DIAG_BIT:
+                            regoff = 0
+                            if reg_positions and dop["kind"] == OP_DIAG_BIT:
                                 regoff = 1 << nthr  # the b0=1 half follows the b0=0 half
-                            else:
+                            elif reg_positions:
                                 regoff = add16(
                                     sum(((j >> R.index(x)) & 1) << (nthr + k) for k, x in enumerate(reg_positions))
                                     for j in range(NR)
@@ -478,10 +485,19 @@ class Planner:
             blob[coef_off : coef_off + inter.nbytes] = inter.tobytes()
         if a64:
             blob[u64_off : u64_off + 8 * len(a64)] = np.asarray(a64, dtype=np.uint64).tobytes()
-        for i, (pieces, toff, regoff) in enumerate(tabdescs):
-            pb = b"".join(struct.pack("<BBBB", s, ln, o, 0) for s, ln, o in pieces)
-            pb += b"\0" * (24 - len(pb))
-            blob[tabdesc_off + 32 * i : tabdesc_off + 32 * i + 32] = pb + struct.pack("<II", toff, regoff)
+        for i, td in enumerate(tabdescs):
+            if td[0] == "mul":
+                _, shift, mask, mult, brev, rsh = td
+                rec = struct.pack("<3xBBBBBIIQQ", 0, shift, brev, rsh, 1, mask, 0, mult, 0)
+            else:
+                pieces, toff, regoff = td
+                pb = b"".join(
+                    struct.pack("<BBBB", s, ln, o, len(pieces) if k == 0 else 0) for k, (s, ln, o) in enumerate(pieces)
+                )
+                pb += b"\0" * (24 - len(pb))
+                rec = pb + struct.pack("<II", toff, regoff)
+            assert len(rec) == 32
+            blob[tabdesc_off + 32 * i : tabdesc_off + 32 * i + 32] = rec
         if a16:
             blob[u16_off : u16_off + 2 * len(a16)] = np.asarray(a16, dtype=np.uint16).tobytes()
         if tables:
@@ -679,25 +695,27 @@ def _build_diag_ops(terms, R, cfg):
         else:
             gen_terms.append((positions, turns))
 
+    frac_bits = 32 if cfg.dtype == QB2_C64 else 64
     thr_tabs = []
     for pset, tterms in _merge_tables(thr_terms, Rset, MAX_TAB_BITS):
         order = sorted(pset)
-        thr_tabs.append((order, _table_values(order, tterms)))
+        thr_tabs.append(("tab", order, _table_values(order, tterms)))
 
     ops = []
     if have_vec and np.any(np.abs(vec - np.rint(vec)) > 0):
         ops.append({"kind": OP_DIAG_VEC, "vec": vec, "thr": [], "reg": []})
     for b in sorted(bit_terms):
-        reg_tabs = []
-        for pset, tterms in _merge_tables(bit_terms[b], Rset, MAX_TAB_BITS):
+        muls, rest = _fit_multipliers(bit_terms[b], R[b], frac_bits)
+        reg_tabs = list(muls)
+        for pset, tterms in _merge_tables(rest, Rset, MAX_TAB_BITS):
             order = sorted(x for x in pset if x not in Rset) + [R[b]]
-            reg_tabs.append((order, _table_values(order, tterms)))
+            reg_tabs.append(("tab", order, _table_values(order, tterms)))
         for s in range(0, len(reg_tabs), 200):
             ops.append({"kind": OP_DIAG_BIT, "b0": b, "thr": [], "reg": reg_tabs[s : s + 200]})
     gen_tabs = []
     for pset, tterms in _merge_tables(gen_terms, Rset, MAX_TAB_BITS):
         order = sorted(x for x in pset if x not in Rset) + sorted((x for x in pset if x in Rset), key=R.index)
-        gen_tabs.append((order, _table_values(order, tterms)))
+        gen_tabs.append(("tab", order, _table_values(order, tterms)))
     for s in range(0, len(gen_tabs), MAX_REG_TABS):
         ops.append({"kind": OP_DIAG, "thr": [], "reg": gen_tabs[s : s + MAX_REG_TABS]})
     # the thread tables ride on the first op that evaluates tables anyway
@@ -708,9 +726,69 @@ def _build_diag_ops(terms, R, cfg):
             ops.append({"kind": OP_DIAG_THR, "thr": chunk, "reg": []})
         else:
             host["thr"] = chunk
+    frac_t = np.uint32 if cfg.dtype == QB2_C64 else np.uint64
     for o in ops:
         if o["kind"] == OP_DIAG_BIT and not o["thr"]:
-            frac_t = np.uint32 if cfg.dtype == QB2_C64 else np.uint64
-            if all(not np.any(_to_frac(v[: len(v) // 2], frac_t)) for _, v in o["reg"]):
+            if all(t[0] == "mul" or not np.any(_to_frac(t[2][: len(t[2]) // 2], frac_t)) for t in o["reg"]):
                 o["flags"] = 1  # the b0=0 phase is exactly zero: skip those amplitudes
     return ops
+
+
+def _fit_multipliers(terms, regpos, frac_bits):
+    """Controlled-phase ladders: terms ``exp(2 pi i theta_a x_b x_a)`` whose angles are
+    geometric in the partner position, ``theta_a = c * 2**(p_a - shift)`` mod 1, need no
+    table: phase = c * (index bits).  Returns (multiplier entries, remaining terms)."""
+    mod = 1 << frac_bits
+    cands, rest = [], []
+    for positions, turns in terms:
+        if len(positions) == 2:
+            ib = positions.index(regpos)
+            t = turns.reshape(2, 2)  # [bit1, bit0]
+            t = t if ib == 1 else t.T  # -> [x_b, x_a]
+            z = np.exp(2j * np.pi * t)
+            if abs(z[0, 0] - 1) < 1e-15 and abs(z[0, 1] - 1) < 1e-15 and abs(z[1, 0] - 1) < 1e-15:
+                a = positions[1 - ib]
+                f = int(np.rint((t[1, 1] - np.floor(t[1, 1])) * 4294967296.0 * (4294967296.0 if frac_bits == 64 else 1.0)))
+                if frac_bits == 64:
+                    f = _frac64(t[1, 1])
+                cands.append((a, f % mod, (positions, turns)))
+                continue
+        rest.append((positions, turns))
+    muls = []
+    cands.sort(key=lambda c: c[0])
+
+    def close(x, y):
+        return abs((x - y + mod // 2) % mod - mod // 2) <= 4
+
+    while cands:
+        shift = cands[0][0]
+        window = [c for c in cands if c[0] - shift < 32]
+        # ascending ladder: theta_a = c0 * 2**(a - shift)
+        c_up = window[0][1]
+        up = [c for c in window if close(c_up << (c[0] - shift), c[1])]
+        # descending ladder: theta_a = c1 * 2**(top - a)
+        top = window[-1][0]
+        c_dn = window[-1][1]
+        dn = [c for c in window if close(c_dn << (top - c[0]), c[1])]
+        group = up if len(up) >= len(dn) else dn
+        if len(group) >= 1:
+            mask = 0
+            for a, _, _ in group:
+                mask |= 1 << (a - shift)
+            if group is up:
+                muls.append(("mul", shift, mask, c_up, 0, 0))
+            else:
+                muls.append(("mul", shift, mask, c_dn, 1, 31 - (top - shift)))
+            ids = {id(c) for c in group}
+            cands = [c for c in cands if id(c) not in ids]
+        else:
+            rest.append(cands[0][2])
+            cands = cands[1:]
+    return muls, rest
+
+
+def _frac64(turn):
+    t = float(turn) - np.floor(float(turn))
+    hi = int(np.floor(t * 4294967296.0))
+    lo = int(np.rint((t * 4294967296.0 - hi) * 4294967296.0))
+    return ((hi << 32) + lo) % (1 << 64)
