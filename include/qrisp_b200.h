@@ -137,6 +137,7 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_MAX_TILE_BITS 13
 #define QB2_MAX_REG_BITS 5
 #define QB2_MAX_SEGS 16
+#define QB2_MAX_PHASES 8
 #define QB2_MAX_SMALL_BYTES 8192
 
 #define QB2_OP_MAT1 1 /* 2x2 on register bit b0 */
@@ -195,7 +196,11 @@ typedef struct qb2_phase { /* 32 bytes */
      * bits, XOR the register entry. */
     uint32_t xw; /* slot map under the PREVIOUS phase's distribution (store side) */
     uint32_t xr; /* slot map under THIS phase's distribution (load side) */
-    uint32_t rsv[2];
+    /* bit 0: on the store side register j sits at slot (j << kw); bit 1: on the load side at
+     * (j << kr): the kernel then uses immediate offsets instead of the register entries.
+     * kw = bits 8..15, kr = bits 16..23. */
+    uint32_t xflags;
+    uint32_t rsv;
 } qb2_phase;
 
 typedef struct qb2_op { /* 32 bytes */

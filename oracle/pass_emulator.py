@@ -33,7 +33,7 @@ def parse(blob):
     P = ParsedPass()
     P.n, P.T, P.r, P.dtype, P.small = n, T, r, dtype, small
     P.segs = [struct.unpack_from("<BBBB", b, 64 + 4 * i)[:3] for i in range(n_seg)]
-    P.phases = [struct.unpack_from("<8I", b, phases_off + 32 * i)[:6] for i in range(n_phases)]
+    P.phases = [struct.unpack_from("<8I", b, phases_off + 32 * i)[:7] for i in range(n_phases)]
     P.ops = []
     for i in range(n_ops):
         cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags = struct.unpack_from("<QQIIBBBBBB", b, ops_off + 32 * i)
@@ -117,23 +117,34 @@ def run(blob, state, hi_base=0, report=None):
         for src, dst, ln in P.segs:
             tbase |= ((t >> src) & ((1 << ln) - 1)) << dst
         ph0 = P.phases[0]
+        assert len(P.phases) <= 8
         xloc = np.uint64(tbase) | thread_cols(ph0[2], P.a64, False)
         rp = P.a64[ph0[3] : ph0[3] + NR]
         addr = xloc[:, None] | rp[None, :]
         regs = state[addr.astype(np.int64)]  # [thread, j]
         seen = np.zeros(1 << T, dtype=bool)
-        for pi, (first_op, nops, pcol, rphys, xw, xr) in enumerate(P.phases):
+        for pi, (first_op, nops, pcol, rphys, xw, xr, xflags) in enumerate(P.phases):
             if pi > 0:
                 tile = np.zeros(1 << T, dtype=cdt)
                 filled = np.zeros(1 << T, dtype=bool)
                 wb = thread_cols(xw, P.a16, True)
-                slots = (wb[:, None] ^ P.a16[xw + TB : xw + TB + NR].astype(np.uint64)[None, :]).astype(np.int64)
+                wreg = P.a16[xw + TB : xw + TB + NR].astype(np.uint64)
+                if xflags & 1:  # the kernel uses j << kw (added, not XORed) instead of the table
+                    kw = (xflags >> 8) & 0xFF
+                    assert np.array_equal(wreg, np.arange(NR, dtype=np.uint64) << np.uint64(kw))
+                    assert not np.any(wb & np.uint64((NR - 1) << kw))
+                slots = (wb[:, None] ^ wreg[None, :]).astype(np.int64)
                 assert slots.max() < (1 << T)
                 assert not filled[slots.reshape(-1)].any() and len(np.unique(slots)) == slots.size, "store slots collide"
                 tile[slots] = regs
                 _check_conflicts(slots, conflict_lanes, report, "store", pi)
                 rb = thread_cols(xr, P.a16, True)
-                slots = (rb[:, None] ^ P.a16[xr + TB : xr + TB + NR].astype(np.uint64)[None, :]).astype(np.int64)
+                rreg = P.a16[xr + TB : xr + TB + NR].astype(np.uint64)
+                if xflags & 2:
+                    kr = (xflags >> 16) & 0xFF
+                    assert np.array_equal(rreg, np.arange(NR, dtype=np.uint64) << np.uint64(kr))
+                    assert not np.any(rb & np.uint64((NR - 1) << kr))
+                slots = (rb[:, None] ^ rreg[None, :]).astype(np.int64)
                 assert len(np.unique(slots)) == slots.size, "load slots collide"
                 regs = tile[slots]
                 _check_conflicts(slots, conflict_lanes, report, "load", pi)

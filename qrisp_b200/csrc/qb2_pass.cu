@@ -204,8 +204,8 @@ __device__ __forceinline__ void mat1_swap(real (&re)[1 << RB], real (&im)[1 << R
 template <typename real, int RB, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
     pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
-                const uint64_t hi_base, const uint32_t ntiles, const uint32_t roots_off, const uint32_t tile_off,
-                const __grid_constant__ PassParams P) {
+                const uint64_t hi_base, const uint32_t ntiles, const uint32_t roots_off, const uint32_t ctx_off,
+                const uint32_t tile_off, const __grid_constant__ PassParams P) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
     constexpr int NR = 1 << RB;
@@ -231,10 +231,32 @@ __global__ void __launch_bounds__(MAXT, MINB)
     const uint16_t *const a16 = reinterpret_cast<const uint16_t *>(pb + H->u16_off);
     const uint64_t *const a64 = reinterpret_cast<const uint64_t *>(pb + H->u64_off);
     const qb2_tab *const tabs = reinterpret_cast<const qb2_tab *>(pb + H->tabdesc_off);
-    vec *const tile = reinterpret_cast<vec *>(smem + tile_off);
     const int TB = (int)H->T - RB;  // thread bits
     const uint32_t n_phases = H->n_phases;
     const int n_seg = H->n_seg;
+
+    // ---- per-thread context of every phase, computed once per CTA: the thread's physical
+    // offset and its shared-memory byte offsets on the store / load side of the exchange that
+    // enters the phase.  Each thread reads back only its own entry.
+    uint4 *const ctx = reinterpret_cast<uint4 *>(smem + ctx_off);
+    const uint32_t nthreads = blockDim.x;
+    for (uint32_t p = 0; p < n_phases; ++p) {
+        const qb2_phase &ph = phases[p];
+        uint64_t xt = 0;
+        uint32_t wb = 0, rb = 0;
+        for (int b = 0; b < TB; ++b)
+            if ((tid >> b) & 1u) {
+                xt |= a64[ph.pcol + b];
+                if (p > 0) {
+                    wb ^= a16[ph.xw + b];
+                    rb ^= a16[ph.xr + b];
+                }
+            }
+        ctx[p * nthreads + tid] =
+            make_uint4((uint32_t)xt, (uint32_t)(xt >> 32), wb * (uint32_t)sizeof(vec), rb * (uint32_t)sizeof(vec));
+    }
+    uint8_t *const tile_b = smem + tile_off;
+    const uint8_t *const state_b = reinterpret_cast<const uint8_t *>(state);
 
     real re[NR], im[NR];
 
@@ -249,14 +271,13 @@ __global__ void __launch_bounds__(MAXT, MINB)
         uint64_t xloc;  // local physical index of this thread's register 0
         {
             const qb2_phase &ph = phases[0];
-            uint64_t xt = 0;
-            for (int b = 0; b < TB; ++b)
-                if ((tid >> b) & 1u) xt |= a64[ph.pcol + b];
-            xloc = tbase | xt;
+            const uint4 c = ctx[tid];
+            xloc = tbase | ((uint64_t)c.y << 32 | c.x);
+            const uint8_t *gb = state_b + xloc * sizeof(vec);
             const uint64_t *rp = a64 + ph.rphys;
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
-                const vec v = ld_stream(state + (xloc | rp[j]));
+                const vec v = ld_stream(reinterpret_cast<const vec *>(gb + rp[j] * sizeof(vec)));
                 re[j] = v.x;
                 im[j] = v.y;
             });
@@ -265,36 +286,52 @@ __global__ void __launch_bounds__(MAXT, MINB)
             const qb2_phase &ph = phases[p];
             if (p > 0) {
                 // ---- exchange through shared memory
+                const uint4 c = ctx[p * nthreads + tid];
+                const uint32_t xf = ph.xflags;
                 {
-                    const uint16_t *xw = a16 + ph.xw;
-                    uint32_t wb = 0;
-                    for (int b = 0; b < TB; ++b)
-                        if ((tid >> b) & 1u) wb ^= xw[b];
-                    static_for<0, NR>([&](auto J) {
-                        constexpr int j = decltype(J)::value;
-                        vec v;
-                        v.x = re[j];
-                        v.y = im[j];
-                        tile[wb ^ xw[TB + j]] = v;
-                    });
+                    uint8_t *wp = tile_b + c.z;
+                    if (xf & 1u) {  // register j sits at slot j << kw: immediate offsets
+                        const uint32_t stride = (uint32_t)sizeof(vec) << (xf >> 8 & 0xffu);
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            vec v;
+                            v.x = re[j];
+                            v.y = im[j];
+                            *reinterpret_cast<vec *>(wp + j * stride) = v;
+                        });
+                    } else {
+                        const uint16_t *xw = a16 + ph.xw + TB;
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            vec v;
+                            v.x = re[j];
+                            v.y = im[j];
+                            *reinterpret_cast<vec *>(tile_b + (c.z ^ (xw[j] * (uint32_t)sizeof(vec)))) = v;
+                        });
+                    }
                 }
                 __syncthreads();
                 {
-                    const uint16_t *xr = a16 + ph.xr;
-                    uint32_t rb = 0;
-                    uint64_t xt = 0;
-                    for (int b = 0; b < TB; ++b)
-                        if ((tid >> b) & 1u) {
-                            rb ^= xr[b];
-                            xt |= a64[ph.pcol + b];
-                        }
-                    xloc = tbase | xt;
-                    static_for<0, NR>([&](auto J) {
-                        constexpr int j = decltype(J)::value;
-                        const vec v = tile[rb ^ xr[TB + j]];
-                        re[j] = v.x;
-                        im[j] = v.y;
-                    });
+                    xloc = tbase | ((uint64_t)c.y << 32 | c.x);
+                    const uint8_t *rp_ = tile_b + c.w;
+                    if (xf & 2u) {
+                        const uint32_t stride = (uint32_t)sizeof(vec) << (xf >> 16 & 0xffu);
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            const vec v = *reinterpret_cast<const vec *>(rp_ + j * stride);
+                            re[j] = v.x;
+                            im[j] = v.y;
+                        });
+                    } else {
+                        const uint16_t *xr = a16 + ph.xr + TB;
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            const vec v =
+                                *reinterpret_cast<const vec *>(tile_b + (c.w ^ (xr[j] * (uint32_t)sizeof(vec))));
+                            re[j] = v.x;
+                            im[j] = v.y;
+                        });
+                    }
                 }
                 __syncthreads();
             }
@@ -444,12 +481,13 @@ __global__ void __launch_bounds__(MAXT, MINB)
         // ---- store with the last phase's distribution
         {
             const uint64_t *rp = a64 + phases[n_phases - 1].rphys;
+            uint8_t *gb = reinterpret_cast<uint8_t *>(state) + xloc * sizeof(vec);
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
                 vec v;
                 v.x = re[j];
                 v.y = im[j];
-                st_stream(state + (xloc | rp[j]), v);
+                st_stream(reinterpret_cast<vec *>(gb + rp[j] * sizeof(vec)), v);
             });
         }
     }
@@ -484,7 +522,8 @@ int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, cons
     static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
     const uint32_t threads = 1u << (h->T - RB);
     const uint32_t roots_off = 0;
-    const uint32_t tile_off = std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0;
+    const uint32_t ctx_off = std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0;
+    const uint32_t tile_off = ctx_off + h->n_phases * threads * 16u;
     const size_t tile_bytes = h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0;
     const size_t smem = tile_off + tile_bytes;
     if (!attr_set) {
@@ -506,7 +545,8 @@ int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, cons
     static PassParams params;
     memcpy(&params, h, h->small_bytes);
     const frac *tables = reinterpret_cast<const frac *>(reinterpret_cast<const uint8_t *>(blob_dev) + h->tab_off);
-    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, hi_base, ntiles, roots_off, tile_off, params);
+    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, hi_base, ntiles, roots_off, ctx_off, tile_off,
+                                     params);
     count_launch();
     return check_cuda(cudaGetLastError(), "pass_kernel launch");
 }
@@ -524,7 +564,8 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
     if (h->n_seg > QB2_MAX_SEGS) return set_error(QB2_ELIMIT, "qb2_run_pass: too many segments");
     if (h->small_bytes > QB2_MAX_SMALL_BYTES || (h->small_bytes & 15u) || h->small_bytes < sizeof(qb2_pass_header))
         return set_error(QB2_ELIMIT, "qb2_run_pass: small section of %u bytes", h->small_bytes);
-    if (h->n_phases < 1) return set_error(QB2_EINVAL, "qb2_run_pass: pass without phases");
+    if (h->n_phases < 1 || h->n_phases > QB2_MAX_PHASES)
+        return set_error(QB2_EINVAL, "qb2_run_pass: %u phases (1..%d allowed)", h->n_phases, QB2_MAX_PHASES);
     if (((uintptr_t)blob_dev & 15u) != 0) return set_error(QB2_EINVAL, "qb2_run_pass: blob not 16-byte aligned");
     if (n - (int)h->T > 31) return set_error(QB2_ELIMIT, "qb2_run_pass: too many tiles");
     const uint32_t ntiles = 1u << (n - h->T);

@@ -35,6 +35,7 @@ OP_MAT = {1: 1, 2: 2, 3: 3, 4: 4}
 OP_DIAG, OP_DIAG_THR, OP_DIAG_BIT, OP_DIAG_VEC = 5, 6, 7, 8
 MAT1_GENERAL, MAT1_REAL, MAT1_ANTI, MAT1_SWAP = 0, 1, 2, 3
 MAX_SEGS = 16
+MAX_PHASES = 8
 MAX_SMALL_BYTES = 8192
 MAX_TAB_BITS = 10
 MAX_PIECES = 6
@@ -293,6 +294,8 @@ class Planner:
             phases.insert(0, [list(default_R), []])
         if set(phases[-1][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
             phases.append([list(default_R), []])
+        if len(phases) > MAX_PHASES:
+            raise DescriptorOverflow(f"{len(phases)} phases in one pass")
         return self._pack(tile_pos, phases)
 
     # -------------------------------------------------------------- packing
@@ -325,12 +328,17 @@ class Planner:
             TP = [x for x in tile_pos if x not in R]
             pcol = add64(1 << x for x in TP)
             rphys = add64(sum(((j >> i) & 1) << R[i] for i in range(r)) for j in range(NR))
-            xw = xr = 0
+            xw = xr = xflags = 0
             if prev is not None:
-                col = _slot_columns(tile_pos, prev[1], TP, cfg.conflict_bits)
                 pR, pTP = prev
+                col = _slot_columns(tile_pos, pR, pTP, R, TP, cfg.conflict_bits)
                 xw = add16([col[x] for x in pTP] + [_xor_cols(col, pR, j) for j in range(NR)])
                 xr = add16([col[x] for x in TP] + [_xor_cols(col, R, j) for j in range(NR)])
+                kw, kr = _regular_shift(col, pR, pTP), _regular_shift(col, R, TP)
+                if kw is not None:
+                    xflags |= 1 | (kw << 8)
+                if kr is not None:
+                    xflags |= 2 | (kr << 16)
             first_op = op_count
             # ---- ops: merge runs of diagonal terms
             i = 0
@@ -404,7 +412,7 @@ class Planner:
                 )
                 op_count += 1
                 i += 1
-            phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, 0, 0))
+            phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
         # ---- segments: tile id bits -> non-tile local positions
@@ -545,13 +553,16 @@ def _permute_matrix(mat, order):
     return np.asarray(mat, dtype=np.complex128)[np.ix_(idx, idx)]
 
 
-def _slot_columns(tile_pos, write_tp, read_tp, conflict_bits):
+def _slot_columns(tile_pos, write_R, write_tp, read_R, read_tp, conflict_bits):
     """Shared-memory slot map of an exchange: XOR-linear in the tile-local index.
 
     Returns ``col[position] -> uint16``; the slot of a tile-local index is the XOR of the
     columns of its set bits.  The map is built so that the ``2**c`` lanes of a wavefront hit
     ``2**c`` different bank groups both when the tile is stored under the old distribution
     (lane bits = ``write_tp[:c]``) and when it is loaded under the new one (``read_tp[:c]``).
+    Above the lane rows come the old register positions, then the new ones, each in register
+    order: when they do not collide with a lane row, register ``j`` simply sits at slot
+    ``j << k`` and the kernel needs no per-register table.
     """
     c = min(conflict_bits, len(write_tp), len(read_tp))
     W = list(write_tp[:c])
@@ -563,7 +574,7 @@ def _slot_columns(tile_pos, write_tp, read_tp, conflict_bits):
     read_only = [x for x in Rr if x not in W]
     assert len(free_rows) == len(read_only)
     nxt = c
-    for x in tile_pos:
+    for x in list(write_R) + list(read_R) + list(tile_pos):
         if x in col:
             continue
         col[x] = 1 << nxt
@@ -571,6 +582,22 @@ def _slot_columns(tile_pos, write_tp, read_tp, conflict_bits):
     for row, x in zip(free_rows, read_only):
         col[x] ^= 1 << row
     return col
+
+
+def _regular_shift(col, R, TP):
+    """k such that register j sits at slot ``j << k`` (columns of R are 1<<k, 1<<(k+1)...) and no
+    thread column touches those slot bits (so that XOR and + agree), else None."""
+    c0 = col[R[0]]
+    if c0 & (c0 - 1):
+        return None
+    k = c0.bit_length() - 1
+    for i, x in enumerate(R):
+        if col[x] != 1 << (k + i):
+            return None
+    span = ((1 << len(R)) - 1) << k
+    if any(col[x] & span for x in TP):
+        return None
+    return k
 
 
 def _xor_cols(col, R, j):
