@@ -1,0 +1,336 @@
+"""Statevector sharded over several GPUs by its high physical positions.
+
+``world = 2**g`` ranks (one process per GPU, ``torch.distributed``); rank ``k`` owns the
+``2**n_local`` amplitudes whose positions ``>= n_local`` spell ``k`` (the "rank bits").
+
+* Diagonal gates and controls on rank bits need no communication: the pass kernel receives
+  the rank bits through ``hi_base`` and evaluates phases / control masks on the full
+  physical index.
+* A dense target on a rank bit triggers a QUBIT SWAP: ``g`` local positions (chosen by
+  furthest next use) trade places with the ``g`` rank bits.  Data movement = one local bit
+  permutation that brings the evicted positions to the top of the local index, then one
+  ``all_to_all_single`` of ``2**g`` contiguous chunks over NCCL / NVLink.  Afterwards only
+  the position map changes.
+
+The reference has no counterpart (its simulator is single-process numpy); this is the
+"statevector too large for one GPU" row of the north star.  The class mirrors
+:class:`qrisp_b200.engine.StateVector` so that ``run`` / ``bench.py`` treat both alike.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .engine import MIN_QUBITS, DeviceOps, Program
+from .normalize import normalize_circuit
+from .planner import QB2_C64, QB2_C128, PlanConfig, Planner
+
+
+class SwapStep:
+    """Trade the rank bits with the local positions ``evict`` (ascending list of g positions)."""
+
+    kind = "swap"
+
+    def __init__(self, evict, perm):
+        self.evict = evict  # local positions that become rank bits
+        self.perm = perm  # local bit permutation applied first (None: evict already on top)
+
+
+def choose_evictions(pending, pos, n_local, g, protect):
+    """The g local positions whose next use as a dense target is furthest away (Belady);
+    positions in ``protect`` (the low, coalescing positions) are never evicted."""
+    where = {p: q for q, p in enumerate(pos)}
+    next_use = {p: len(pending) + 1 for p in range(n_local) if p not in protect}
+    for i, op in enumerate(pending):
+        if op.kind == "relabel":
+            break  # the map changes from here on; keep what we know
+        for q in op.nd:
+            p = pos[q]
+            if p in next_use and next_use[p] > i:
+                next_use[p] = i
+    order = sorted(next_use, key=lambda p: (-next_use[p], -p))
+    return sorted(order[:g])
+
+
+class ShardedStateVector(DeviceOps):
+    def __init__(self, num_qubits, group=None, dtype=np.complex64, device=None, T=None, r=None, L=4):
+        import torch
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        g = self.world.bit_length() - 1
+        if 1 << g != self.world:
+            raise ValueError("the number of ranks must be a power of two")
+        self.g = g
+        self.num_qubits = int(num_qubits)
+        self.n_total = max(self.num_qubits, MIN_QUBITS + g)
+        self.n = self.n_total - g  # local positions
+        if self.n < 2 * g + L:
+            raise ValueError("too few local qubits for this many ranks")
+        dtype = np.dtype(dtype)
+        if dtype == np.complex64:
+            self.dtype, self.np_dtype = QB2_C64, np.complex64
+        elif dtype == np.complex128:
+            self.dtype, self.np_dtype = QB2_C128, np.complex128
+        else:
+            raise TypeError(f"unsupported amplitude dtype {dtype}")
+        self.cfg = PlanConfig(self.n, self.dtype, T=T, r=r, L=L)
+        nq = self.num_qubits
+        self.pos = [nq - 1 - q for q in range(nq)] + list(range(nq, self.n_total))
+        self.hi_base = self.rank << self.n
+        self.stats = {"passes": 0, "kernel_ops": 0, "gate_ops": 0, "phases": 0, "big": 0, "swaps": 0}
+        self.io = {"h2d": 0, "d2h": 0}
+        self._setup_device(device)
+        self.reset()
+
+    # ------------------------------------------------------------------ device hooks
+    # (tests replace these with CPU stand-ins to exercise the sharding logic over gloo)
+    def _setup_device(self, device):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise _lib.Qb2Error("the B200 engine needs a CUDA device; there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        torch.cuda.set_device(self.device)
+        real = torch.float32 if self.dtype == QB2_C64 else torch.float64
+        self.state = torch.empty(2 << self.n, dtype=real, device=self.device)
+        self._scratch = torch.empty_like(self.state)
+
+    def _scratch_buf(self):
+        return self._scratch
+
+    def reset(self):
+        basis = 0 if self.rank == 0 else _lib.QB2_NO_BASIS
+        _lib.check(self.lib.qb2_init_basis(self.state.data_ptr(), self.n, basis, self.dtype, self._stream()), "qb2_init_basis")
+
+    def _permute_local(self, perm):
+        arr = (ctypes.c_int * self.n)(*perm)
+        _lib.check(
+            self.lib.qb2_permute_bits(self.state.data_ptr(), self._scratch.data_ptr(), self.n, arr, self.dtype, self._stream()),
+            "qb2_permute_bits",
+        )
+        self.state, self._scratch = self._scratch, self.state
+
+    def _all_to_all(self):
+        """state (2**g contiguous chunks) -> scratch: chunk c goes to rank c."""
+        self.dist.all_to_all_single(self._scratch, self.state, group=self.group)
+        self.state, self._scratch = self._scratch, self.state
+
+    def synchronize(self):
+        import torch
+
+        torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------ planning
+    def compile(self, instructions):
+        unit_tol = 1e-6 if self.dtype == QB2_C64 else 1e-13
+        ops = normalize_circuit(instructions, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
+        return self.compile_ops(ops)
+
+    def compile_ops(self, ops):
+        """Plan with swaps.  ``self.pos`` is advanced to the map after the program."""
+        planner = Planner(self.cfg, self.pos, n_total=self.n_total)
+        steps = []
+        pending = list(ops)
+        protect = set(range(self.cfg.L))
+        guard = 0
+        while pending:
+            part, need = planner.plan(pending)
+            steps.extend(part)
+            if need is None:
+                break
+            pending = planner.pending
+            guard += 1
+            if guard > 10000:
+                raise RuntimeError("swap planning does not terminate")
+            steps.append(self._plan_swap(pending, protect))
+        return ShardedProgram(self, steps)
+
+    def _plan_swap(self, pending, protect):
+        n, g = self.n, self.g
+        evict = choose_evictions(pending, self.pos, n, g, protect)
+        # local permutation that moves evict[i] to position n-g+i and keeps the others in order
+        keep = [p for p in range(n) if p not in evict]
+        perm = [0] * n  # bit perm[p] of the new index = bit p of the old one
+        for newp, oldp in enumerate(keep + evict):
+            perm[oldp] = newp
+        identity = all(perm[p] == p for p in range(n))
+        # relabel: first the local permutation, then top-local <-> rank bits
+        newpos = {}
+        for q, p in enumerate(self.pos):
+            if p < n:
+                p2 = perm[p]
+                newpos[q] = p2 + g if p2 >= n - g else p2  # evicted positions become rank bits
+            else:
+                newpos[q] = p - g  # rank bits land on the top local positions
+        for q in range(len(self.pos)):
+            self.pos[q] = newpos[q]
+        return SwapStep(evict, None if identity else perm)
+
+    def apply_circuit(self, instructions):
+        prog = self.compile(instructions)
+        prog.run()
+        return prog
+
+    # ------------------------------------------------------------------ execution of one swap
+    def run_swap(self, step):
+        if step.perm is not None:
+            self._permute_local(step.perm)
+        self._all_to_all()
+        self.stats["swaps"] += 1
+
+    # ------------------------------------------------------------------ read-out
+    def probabilities(self, qubits):
+        import torch
+
+        m = len(qubits)
+        if m > 30:
+            raise MemoryError(f"a dense distribution over {m} qubits does not fit; sample shots instead")
+        probs = torch.zeros(1 << m, dtype=torch.float64, device=self.device)
+        mes = (ctypes.c_int * max(m, 1))(*[self.pos[q] for q in qubits])
+        _lib.check(
+            self.lib.qb2_probabilities(self.state.data_ptr(), self.n, self.hi_base, mes, m, probs.data_ptr(), self.dtype, self._stream()),
+            "qb2_probabilities",
+        )
+        self.dist.all_reduce(probs, group=self.group)
+        self.io["d2h"] += probs.numel() * 8
+        return probs.cpu().numpy()
+
+    def norm2(self):
+        import torch
+
+        out = torch.empty(1, dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.qb2_norm2(self.state.data_ptr(), self.n, out.data_ptr(), self.dtype, self._stream()), "qb2_norm2")
+        self.dist.all_reduce(out, group=self.group)
+        return float(out.item())
+
+    def sample(self, shots, qubits=None, rng=None):
+        """Every rank draws its share of the shots from its shard; rank weights come from an
+        all-gather of the shard norms.  All ranks must pass identically seeded ``rng``s.
+        Returns the outcome integers on every rank (gathered)."""
+        import torch
+
+        rng = np.random.default_rng(0) if rng is None else rng
+        if qubits is None:
+            qubits = list(range(self.num_qubits))
+        shots = int(shots)
+        cb = self.lib.qb2_sample_chunk_bits(self.n)
+        sums = torch.empty(1 << (self.n - cb), dtype=torch.float64, device=self.device)
+        _lib.check(
+            self.lib.qb2_sample_prepare(self.state.data_ptr(), self.n, sums.data_ptr(), self.dtype, self._stream()),
+            "qb2_sample_prepare",
+        )
+        weights = torch.zeros(self.world, dtype=torch.float64, device=self.device)
+        weights[self.rank] = sums[-1]
+        self.dist.all_reduce(weights, group=self.group)
+        w = weights.cpu().numpy()
+        split = rng.multinomial(shots, w / w.sum())  # same on every rank (same seed)
+        uniforms = rng.random(shots)
+        lo = int(split[: self.rank].sum())
+        mine = np.ascontiguousarray(uniforms[lo : lo + int(split[self.rank])])
+        phys_all = torch.zeros(shots, dtype=torch.int64, device=self.device)
+        if len(mine):
+            u_dev = torch.from_numpy(mine).to(self.device)
+            _lib.check(
+                self.lib.qb2_sample_draw(
+                    self.state.data_ptr(), self.n, sums.data_ptr(), u_dev.data_ptr(), len(mine),
+                    phys_all[lo : lo + len(mine)].data_ptr(), self.dtype, self._stream(),
+                ),
+                "qb2_sample_draw",
+            )
+            phys_all[lo : lo + len(mine)] |= self.hi_base
+        self.dist.all_reduce(phys_all, group=self.group)  # disjoint slices: a sum is a gather
+        self.io["h2d"] += mine.nbytes
+        self.io["d2h"] += shots * 8
+        phys = phys_all.cpu().numpy().astype(np.uint64)
+        m = len(qubits)
+        out = np.zeros(phys.shape, dtype=np.uint64)
+        for k, q in enumerate(qubits):
+            out |= ((phys >> np.uint64(self.pos[q])) & np.uint64(1)) << np.uint64(m - 1 - k)
+        return out
+
+    def statevector(self):
+        """Gather the whole state in canonical order on every rank (small registers only)."""
+        import torch
+
+        if self.n_total > 30:
+            raise MemoryError("statevector(): the gathered state would not fit on one device")
+        shards = [torch.empty_like(self.state) for _ in range(self.world)]
+        self.dist.all_gather(shards, self.state, group=self.group)
+        full = torch.cat(shards).cpu().numpy().view(self.np_dtype)
+        return _canonical(full, self.pos, self.num_qubits)
+
+
+def _canonical(full, pos, nq):
+    N = len(pos)
+    j = np.arange(1 << N, dtype=np.int64)
+    i = np.zeros_like(j)
+    for q in range(N):
+        i |= ((j >> pos[q]) & 1) << (nq - 1 - q if q < nq else q)
+    out = np.empty_like(full)
+    out[i] = full
+    return out[: 1 << nq].copy()
+
+
+class ShardedProgram(Program):
+    """Passes + swaps.  Pass blobs are uploaded once; swaps run on the same stream."""
+
+    def __init__(self, sv, steps):
+        self._swap_steps = [s for s in steps if s.kind == "swap"]
+        super().__init__(sv, steps)
+        self.n_swaps = len(self._swap_steps)
+        self.comm_ms = None
+
+    def run(self, time_comm=False):
+        sv = self.sv
+        comm = []
+        for s, o, h in zip(self.steps, self.offsets, self._headers):
+            if s.kind == "pass":
+                sv._run_pass(s, h, self.dev, o)
+            elif s.kind == "swap":
+                if time_comm:
+                    import torch
+
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    sv.run_swap(s)
+                    e1.record()
+                    comm.append((e0, e1))
+                else:
+                    sv.run_swap(s)
+            else:
+                sv._run_big(s)
+        if time_comm:
+            import torch
+
+            torch.cuda.synchronize()
+            self.comm_ms = sum(a.elapsed_time(b) for a, b in comm)
+        sv.stats["passes"] += self.n_passes
+        sv.stats["kernel_ops"] += self.n_kernel_ops
+        sv.stats["gate_ops"] += self.n_gate_ops
+        sv.stats["phases"] += self.n_phases
+
+
+def sample_counts_sharded(qc, shots, seed=0, group=None, dtype=np.complex64, **engine_kwargs):
+    """Multi-GPU counterpart of :func:`qrisp_b200.simulator.sample_counts`: every rank calls
+    it with the same arguments; the counts dict is returned on every rank."""
+    from .circuit import Circuit
+    from .preprocess import unitarize
+
+    qc = qc if isinstance(qc, Circuit) else Circuit.from_qrisp(qc)
+    instrs, n, measurements = unitarize(qc)
+    sv = ShardedStateVector(n, group=group, dtype=dtype, **engine_kwargs)
+    sv.apply_circuit(instrs)
+    measurements.sort(key=lambda x: -x[1])
+    mes_qubits = [q for q, _ in measurements]
+    outs = sv.sample(int(shots), mes_qubits, rng=np.random.default_rng(seed))
+    vals, counts = np.unique(outs, return_counts=True)
+    width = len(mes_qubits)
+    return {bin(int(v))[2:].zfill(width): int(c) for v, c in zip(vals, counts)}, sv

@@ -26,7 +26,52 @@ def _torch():
     return torch
 
 
-class StateVector:
+class DeviceOps:
+    """How a state object talks to libqb2.so; shared by the single-device and the sharded
+    state.  (CPU tests of the sharding logic substitute these four methods.)"""
+
+    def _stream(self):
+        return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _upload_blobs(self, steps, offs, total):
+        torch = _torch()
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        for s, o in zip(steps, offs):
+            if o is not None:
+                hv[o : o + len(s.blob)] = np.frombuffer(s.blob, dtype=np.uint8)
+        dev = host.to(self.device, non_blocking=True)
+        self._pinned = host  # keep the staging buffer alive until the copy has run
+        self.io["h2d"] += total
+        return dev
+
+    def _run_pass(self, step, header, dev, offset):
+        _lib.check(
+            self.lib.qb2_run_pass(
+                self.state.data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream()
+            ),
+            "qb2_run_pass",
+        )
+
+    def _run_big(self, s):
+        torch = _torch()
+        k = len(s.positions)
+        m = np.ascontiguousarray(s.matrix, dtype=self.np_dtype)
+        m_dev = torch.from_numpy(m.view(np.float32 if self.dtype == QB2_C64 else np.float64).reshape(-1)).to(self.device)
+        tg = (ctypes.c_int * k)(*s.positions)
+        dst = self._scratch_buf()
+        _lib.check(
+            self.lib.qb2_apply_matrix_big(
+                self.state.data_ptr(), dst.data_ptr(), self.n, self.hi_base, m_dev.data_ptr(), tg, k, s.cmask, s.cval,
+                self.dtype, self._stream(),
+            ),
+            "qb2_apply_matrix_big",
+        )
+        self.state, self._scratch = dst, self.state
+        self.stats["big"] += 1
+
+
+class StateVector(DeviceOps):
     """``num_qubits`` logical qubits in |0...0>.
 
     ``pos[q]`` is the physical position (bit of the array index) of logical qubit ``q``;
@@ -195,7 +240,6 @@ class Program:
     """A planned list of steps with its pass blobs resident on the device."""
 
     def __init__(self, sv, steps):
-        torch = _torch()
         self.sv = sv
         self.steps = steps
         offs, total = [], 0
@@ -207,17 +251,8 @@ class Program:
                 offs.append(None)
         self.offsets = offs
         self.h2d_bytes = total
-        self.dev = None
+        self.dev = sv._upload_blobs(steps, offs, total) if total else None
         self._headers = []
-        if total:
-            host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
-            hv = host.numpy()
-            for s, o in zip(steps, offs):
-                if o is not None:
-                    hv[o : o + len(s.blob)] = np.frombuffer(s.blob, dtype=np.uint8)
-            self.dev = host.to(sv.device, non_blocking=True)
-            self._host = host
-            sv.io["h2d"] += total
         for s in steps:
             # the small section (header.small_bytes) is handed to the launch by value
             if s.kind == "pass":
@@ -227,40 +262,19 @@ class Program:
                 self._headers.append(None)
         self.n_passes = sum(1 for s in steps if s.kind == "pass")
         self.n_kernel_ops = sum(s.n_ops for s in steps if s.kind == "pass")
-        self.n_gate_ops = sum(s.n_gate_ops for s in steps if s.kind == "pass") + sum(1 for s in steps if s.kind != "pass")
+        self.n_gate_ops = sum(s.n_gate_ops for s in steps if s.kind == "pass") + sum(1 for s in steps if s.kind == "big")
         self.n_phases = sum(s.n_phases for s in steps if s.kind == "pass")
 
     def run(self):
         sv = self.sv
-        lib = sv.lib
-        stream = sv._stream()
-        base = self.dev.data_ptr() if self.dev is not None else 0
         for s, o, h in zip(self.steps, self.offsets, self._headers):
             if s.kind == "pass":
-                _lib.check(
-                    lib.qb2_run_pass(sv.state.data_ptr(), sv.n, sv.hi_base, h, base + o, sv.dtype, stream), "qb2_run_pass"
-                )
+                sv._run_pass(s, h, self.dev, o)
             else:
-                self._run_big(s, stream)
+                sv._run_big(s)
         sv.stats["passes"] += self.n_passes
         sv.stats["kernel_ops"] += self.n_kernel_ops
         sv.stats["gate_ops"] += self.n_gate_ops
         sv.stats["phases"] += self.n_phases
 
-    def _run_big(self, s, stream):
-        torch = _torch()
-        sv = self.sv
-        k = len(s.positions)
-        m = np.ascontiguousarray(s.matrix, dtype=sv.np_dtype)
-        m_dev = torch.from_numpy(m.view(np.float32 if sv.dtype == QB2_C64 else np.float64).reshape(-1)).to(sv.device)
-        tg = (ctypes.c_int * k)(*s.positions)
-        dst = sv._scratch_buf()
-        _lib.check(
-            sv.lib.qb2_apply_matrix_big(
-                sv.state.data_ptr(), dst.data_ptr(), sv.n, sv.hi_base, m_dev.data_ptr(), tg, k, s.cmask, s.cval, sv.dtype,
-                stream,
-            ),
-            "qb2_apply_matrix_big",
-        )
-        sv.state, sv._scratch = dst, sv.state
-        sv.stats["big"] += 1
+

@@ -268,3 +268,20 @@ def test_full_size_30_qubits_properties():
     # sampling labels at full width
     outs = sv.sample(64, list(range(n)), rng=np.random.default_rng(1))
     assert set(int(o) for o in outs) <= {0, (1 << n) - 1}
+
+
+def test_multi_gpu_sharded_path():
+    """Needs >= 2 GPUs on the box: launches tests/dist_gpu_check.py under torchrun."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "dist_gpu_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "dist_gpu_check ok" in res.stdout
