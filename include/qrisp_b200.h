@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QB2_ABI_VERSION 3
+#define QB2_ABI_VERSION 4
 
 #define QB2_C64 0
 #define QB2_C128 1
@@ -154,6 +154,15 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
                              flags&1: the b0=0 phase is exactly 0 and is skipped */
 #define QB2_OP_DIAG_VEC 8 /* depends on register bits only: 2**r host-computed unit complex factors at `data` */
 
+/* The QFT / FFT butterfly: a 2x2 gate on register bit b0 (no controls), then a phase on the
+ * b0=1 output only: out1 *= w1 * v[pair], w1 = exp(2 pi i * sum of the op's `ntab_reg` bit
+ * tables, b0=1 entries) evaluated once per thread, v[pair] = 2**(r-1) host-computed unit
+ * factors that follow the 4 matrix coefficients at `data`.  Tables start at `tab`. */
+#define QB2_OP_BFLY 9
+#define QB2_BFLY_REAL 1 /* flags: the 2x2 block is real */
+#define QB2_BFLY_V 2    /* flags: v[] present (else 1) */
+#define QB2_BFLY_W 4    /* flags: tables present (else w1 = 1) */
+
 /* qb2_op.flags of a QB2_OP_MAT1: the shape of the 2x2 block (all use the same 4 coefficients) */
 #define QB2_MAT1_GENERAL 0
 #define QB2_MAT1_REAL 1 /* all four entries real (H, RY, X...) */
@@ -215,7 +224,7 @@ typedef struct qb2_op { /* 32 bytes */
     uint8_t ntab_thr; /* DIAG: tables that depend on thread/tile bits only (come first) */
     uint8_t ntab_reg; /* DIAG: tables that also depend on register bits */
     uint8_t flags;
-    uint8_t rsv[2];
+    uint16_t tab;     /* BFLY: first table descriptor (index from tabdesc_off) */
 } qb2_op;
 
 typedef struct qb2_piece { /* ((x >> shift) & ((1 << len) - 1)) << out */

@@ -36,9 +36,9 @@ def parse(blob):
     P.phases = [struct.unpack_from("<8I", b, phases_off + 32 * i)[:7] for i in range(n_phases)]
     P.ops = []
     for i in range(n_ops):
-        cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags = struct.unpack_from("<QQIIBBBBBB", b, ops_off + 32 * i)
+        cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags, tab = struct.unpack_from("<QQIIBBBBBBH", b, ops_off + 32 * i)
         P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, kind=kind, b0=b0, b1=b1, nthr=nthr, nreg=nreg,
-                          flags=flags))
+                          flags=flags, tab=tab))
     real_t = np.float32 if dtype == 0 else np.float64
     frac_t = np.uint32 if dtype == 0 else np.uint64
     P.real_t, P.frac_t = real_t, frac_t
@@ -152,7 +152,32 @@ def run(blob, state, hi_base=0, report=None):
             X = np.uint64(hi_base) | xloc
             for o in range(first_op, first_op + nops):
                 op = P.ops[o]
-                if op["kind"] >= 5:
+                if op["kind"] == 9:  # BFLY
+                    b0, fl = op["b0"], op["flags"]
+                    cf = P.coefs[2 * op["data"] : 2 * op["data"] + 8 + NR].astype(np.float64)
+                    m = (cf[0:8:2] + 1j * cf[1:8:2]).reshape(2, 2)
+                    if fl & 1:
+                        m = m.real.astype(np.complex128)
+                    v = cf[8::2] + 1j * cf[9::2]
+                    s1 = np.zeros(nthreads, dtype=P.frac_t)
+                    if fl & 4:
+                        for tdesc in P.tabs[op["tab"] : op["tab"] + op["nreg"]]:
+                            if "mul" in tdesc:
+                                s1 = s1 + _mul_phase(tdesc, X, P.frac_t)
+                            else:
+                                e = (np.uint64(tdesc["off"]) + _tab_index(tdesc, X)).astype(np.int64)
+                                s1 = s1 + P.tables[e + tdesc["regoff"]]
+                    w1 = _phase(s1, P.dtype) if fl & 4 else np.ones(nthreads, dtype=np.complex128)
+                    new = regs.copy()
+                    for g in range(NR // 2):
+                        j0 = ((g >> b0) << (b0 + 1)) | (g & ((1 << b0) - 1))
+                        j1 = j0 | (1 << b0)
+                        x0, x1 = regs[:, j0].astype(np.complex128), regs[:, j1].astype(np.complex128)
+                        c = w1 * (v[g] if fl & 2 else 1.0)
+                        new[:, j0] = (m[0, 0] * x0 + m[0, 1] * x1).astype(cdt)
+                        new[:, j1] = ((m[1, 0] * x0 + m[1, 1] * x1) * c).astype(cdt)
+                    regs = new
+                elif op["kind"] >= 5:
                     kind = op["kind"]
                     tb = P.tabs[op["data"] : op["data"] + op["nthr"] + op["nreg"]] if kind != 8 else []
                     s = np.zeros(nthreads, dtype=P.frac_t)

@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
             const uint4 c = ctx[tid];
             xloc = tbase | ((uint64_t)c.y << 32 | c.x);
             const uint8_t *gb = state_b + xloc * sizeof(vec);
+            asm volatile("" : "+l"(gb));  // keep base + uniform offset: two adds per address
             const uint64_t *rp = a64 + ph.rphys;
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
@@ -341,7 +342,60 @@ __global__ void __launch_bounds__(MAXT, MINB)
             for (uint32_t o = ph.first_op; o < op_end; ++o) {
                 const qb2_op &op = ops[o];
                 const uint32_t kind = op.kind;
-                if (kind >= QB2_OP_DIAG) {
+                if (kind == QB2_OP_BFLY) {
+                    // 2x2 gate on register bit b0, then a phase on its b0=1 output that depends on
+                    // the other register bits (host-computed v[pair]) and on the thread (w1)
+                    const uint32_t fl = op.flags;
+                    vec w1;
+                    w1.x = 1;
+                    w1.y = 0;
+                    if (fl & QB2_BFLY_W) {
+                        const qb2_tab *tb = tabs + op.tab;
+                        const int nreg = op.ntab_reg;
+                        frac s1 = 0;
+                        for (int i = 0; i < nreg; ++i)
+                            s1 += tab_is_mul(tb[i])
+                                      ? tab_mul<frac>(tb[i], X)
+                                      : __ldg(tables + tb[i].off + tab_index(tb[i], X) + tb[i].regoff);
+                        w1 = unit_phase(s1, roots);
+                    }
+                    const real *m = coefs + 2 * (size_t)op.data;
+                    const real *v = m + 8;
+                    const bool has_v = (fl & QB2_BFLY_V) != 0;
+                    const bool is_real = (fl & QB2_BFLY_REAL) != 0;
+                    const int b0 = op.b0;
+                    static_for<0, RB>([&](auto B) {
+                        constexpr int bb = decltype(B)::value;
+                        if (b0 == bb) {
+                            static_for<0, NR / 2>([&](auto G) {
+                                constexpr int g = decltype(G)::value;
+                                constexpr int j0 = ((g >> bb) << (bb + 1)) | (g & ((1 << bb) - 1));
+                                constexpr int j1 = j0 | (1 << bb);
+                                const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
+                                real tr, ti;
+                                if (is_real) {
+                                    re[j0] = fma(m[0], x0r, m[2] * x1r);
+                                    im[j0] = fma(m[0], x0i, m[2] * x1i);
+                                    tr = fma(m[4], x0r, m[6] * x1r);
+                                    ti = fma(m[4], x0i, m[6] * x1i);
+                                } else {
+                                    re[j0] = fma(m[0], x0r, fma(-m[1], x0i, fma(m[2], x1r, -m[3] * x1i)));
+                                    im[j0] = fma(m[0], x0i, fma(m[1], x0r, fma(m[2], x1i, m[3] * x1r)));
+                                    tr = fma(m[4], x0r, fma(-m[5], x0i, fma(m[6], x1r, -m[7] * x1i)));
+                                    ti = fma(m[4], x0i, fma(m[5], x0r, fma(m[6], x1i, m[7] * x1r)));
+                                }
+                                real cr = w1.x, ci = w1.y;
+                                if (has_v) {
+                                    const real vr = v[2 * g], vi = v[2 * g + 1];
+                                    cr = fma(w1.x, vr, -w1.y * vi);
+                                    ci = fma(w1.x, vi, w1.y * vr);
+                                }
+                                re[j1] = fma(tr, cr, -ti * ci);
+                                im[j1] = fma(tr, ci, ti * cr);
+                            });
+                        }
+                    });
+                } else if (kind >= QB2_OP_DIAG) {
                     const qb2_tab *tb = tabs + op.data;
                     frac sum = 0;
                     const int nthr = op.ntab_thr;
@@ -482,6 +536,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
         {
             const uint64_t *rp = a64 + phases[n_phases - 1].rphys;
             uint8_t *gb = reinterpret_cast<uint8_t *>(state) + xloc * sizeof(vec);
+            asm volatile("" : "+l"(gb));
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
                 vec v;

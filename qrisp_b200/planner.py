@@ -34,6 +34,8 @@ QB2_C64, QB2_C128 = 0, 1
 OP_MAT = {1: 1, 2: 2, 3: 3, 4: 4}
 OP_DIAG, OP_DIAG_THR, OP_DIAG_BIT, OP_DIAG_VEC = 5, 6, 7, 8
 MAT1_GENERAL, MAT1_REAL, MAT1_ANTI, MAT1_SWAP = 0, 1, 2, 3
+OP_BFLY = 9
+BFLY_REAL, BFLY_V, BFLY_W = 1, 2, 4
 MAX_SEGS = 16
 MAX_PHASES = 8
 MAX_SMALL_BYTES = 8192
@@ -64,6 +66,7 @@ class PlanConfig:
         # lanes that one shared-memory wavefront covers: 16 for 8-byte, 8 for 16-byte amplitudes
         self.conflict_bits = 4 if dtype == QB2_C64 else 3
         self.max_mat = min(self.r, 4)  # widest dense op the pass kernel applies in registers
+        self.fuse_bfly = os.environ.get("QB2_NO_BFLY") is None
 
     @property
     def TB(self):
@@ -340,48 +343,58 @@ class Planner:
                 if kr is not None:
                     xflags |= 2 | (kr << 16)
             first_op = op_count
-            # ---- ops: merge runs of diagonal terms
+            # ---- ops: merge runs of diagonal terms; fuse "2x2 gate + phases on its 1-output"
+            def emit_tables(dop):
+                nonlocal n_tab_entries
+                for tab in dop["thr"] + dop["reg"]:
+                    if tab[0] == "mul":
+                        tabdescs.append(tab)
+                        continue
+                    _, positions, vals = tab
+                    thr_positions = [x for x in positions if x not in R]
+                    reg_positions = [x for x in positions if x in R]
+                    nthr = len(thr_positions)
+                    regoff = 0
+                    if reg_positions and dop["kind"] == OP_DIAG_BIT:
+                        regoff = 1 << nthr  # the b0=1 half follows the b0=0 half
+                    elif reg_positions:
+                        regoff = add16(
+                            sum(((j >> R.index(x)) & 1) << (nthr + k) for k, x in enumerate(reg_positions))
+                            for j in range(NR)
+                        )
+                    tabdescs.append((_pieces(thr_positions), n_tab_entries, regoff))
+                    tables.append(_to_frac(vals, frac_t))
+                    n_tab_entries += len(vals)
+
+            def emit_diag(dop):
+                nonlocal op_count
+                data = len(tabdescs)
+                if dop["kind"] == OP_DIAG_VEC:
+                    data = len(coefs)
+                    coefs.extend(np.exp(2j * np.pi * dop["vec"]))
+                emit_tables(dop)
+                ops_b.append(
+                    struct.pack(
+                        "<QQIIBBBBBBH", 0, 0, 0, data, dop["kind"], dop.get("b0", 0), 0, len(dop["thr"]),
+                        len(dop["reg"]), dop.get("flags", 0), 0,
+                    )
+                )
+                op_count += 1
+
+            def diag_run(start):
+                j = start
+                while j < len(pops) and pops[j][0] == "diag":
+                    j += 1
+                return pops[start:j], j
+
             i = 0
             while i < len(pops):
                 op = pops[i]
                 if op[0] == "diag":
-                    terms = []
-                    while i < len(pops) and pops[i][0] == "diag":
-                        terms.append(pops[i])
-                        i += 1
+                    terms, i = diag_run(i)
                     n_gate_ops += len(terms)
                     for dop in _build_diag_ops(terms, R, cfg):
-                        first_tab = len(tabdescs)
-                        data = first_tab
-                        if dop["kind"] == OP_DIAG_VEC:
-                            data = len(coefs)
-                            coefs.extend(np.exp(2j * np.pi * dop["vec"]))
-                        for tab in dop["thr"] + dop["reg"]:
-                            if tab[0] == "mul":
-                                tabdescs.append(tab)
-                                continue
-                            _, positions, vals = tab
-                            thr_positions = [x for x in positions if x not in R]
-                            reg_positions = [x for x in positions if x in R]
-                            nthr = len(thr_positions)
-                            regoff = 0
-                            if reg_positions and dop["kind"] == OP_DIAG_BIT:
-                                regoff = 1 << nthr  # the b0=1 half follows the b0=0 half
-                            elif reg_positions:
-                                regoff = add16(
-                                    sum(((j >> R.index(x)) & 1) << (nthr + k) for k, x in enumerate(reg_positions))
-                                    for j in range(NR)
-                                )
-                            tabdescs.append((_pieces(thr_positions), n_tab_entries, regoff))
-                            tables.append(_to_frac(vals, frac_t))
-                            n_tab_entries += len(vals)
-                        ops_b.append(
-                            struct.pack(
-                                "<QQIIBBBBBB2x", 0, 0, 0, data, dop["kind"], dop.get("b0", 0), 0, len(dop["thr"]),
-                                len(dop["reg"]), dop.get("flags", 0),
-                            )
-                        )
-                        op_count += 1
+                        emit_diag(dop)
                     continue
                 _, tg, mat, ctrls = op
                 n_gate_ops += 1
@@ -392,6 +405,47 @@ class Planner:
                     assert sorted(bits) == list(range(k)), "3/4-qubit dense ops sit on register bits 0..k-1"
                 m = _permute_matrix(mat, order)
                 sbits = sorted(bits)
+                i += 1
+                if k == 1 and not ctrls and cfg.fuse_bfly:
+                    # butterfly: the phases that follow and vanish for b0=0 ride on the gate
+                    terms, nxt = diag_run(i)
+                    if terms:
+                        b0 = sbits[0]
+                        dops = _build_diag_ops(terms, R, cfg)
+                        vec_op = next((d for d in dops if d["kind"] == OP_DIAG_VEC), None)
+                        if vec_op is not None:
+                            t = vec_op["vec"]
+                            zero_half = [j for j in range(NR) if not (j >> b0) & 1]
+                            if np.any(np.abs(t[zero_half] - np.rint(t[zero_half])) > 0):
+                                vec_op = None
+                        bit_op = next(
+                            (d for d in dops if d["kind"] == OP_DIAG_BIT and d["b0"] == b0 and d.get("flags", 0) & 1
+                             and len(d["reg"]) <= 255), None)
+                        if vec_op is not None or bit_op is not None:
+                            n_gate_ops += len(terms)
+                            i = nxt
+                            flags = BFLY_REAL if np.max(np.abs(m.imag)) < 1e-16 else 0
+                            data = len(coefs)
+                            coefs.extend(m.reshape(-1))
+                            if vec_op is not None:
+                                flags |= BFLY_V
+                                pairs = [((g >> b0) << (b0 + 1)) | (g & ((1 << b0) - 1)) | (1 << b0) for g in range(NR // 2)]
+                                coefs.extend(np.exp(2j * np.pi * vec_op["vec"][pairs]))
+                            else:
+                                coefs.extend(np.ones(NR // 2, dtype=np.complex128))
+                            tab0 = len(tabdescs)
+                            ntab = 0
+                            if bit_op is not None:
+                                flags |= BFLY_W
+                                emit_tables(bit_op)
+                                ntab = len(bit_op["reg"])
+                            assert tab0 < 65536
+                            ops_b.append(struct.pack("<QQIIBBBBBBH", 0, 0, 0, data, OP_BFLY, b0, 0, 0, ntab, flags, tab0))
+                            op_count += 1
+                            for d in dops:
+                                if d is not vec_op and d is not bit_op:
+                                    emit_diag(d)
+                            continue
                 cmask = cval = 0
                 jmask = 0
                 regc = {R.index(p): v for p, v in ctrls.items() if p in R}
@@ -406,12 +460,11 @@ class Planner:
                 coefs.extend(m.reshape(-1))
                 ops_b.append(
                     struct.pack(
-                        "<QQIIBBBBBB2x", cmask, cval, jmask, data, OP_MAT[k], sbits[0], sbits[1] if k > 1 else 0, 0, 0,
-                        _mat1_shape(m) if k == 1 else 0,
+                        "<QQIIBBBBBBH", cmask, cval, jmask, data, OP_MAT[k], sbits[0], sbits[1] if k > 1 else 0, 0, 0,
+                        _mat1_shape(m) if k == 1 else 0, 0,
                     )
                 )
                 op_count += 1
-                i += 1
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
