@@ -1,7 +1,7 @@
 # Builds libqb2.so (the CUDA engine behind include/qrisp_b200.h) for sm_100a, and the C oracle.
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude -Iqrisp_b200/csrc
+NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude -Iqrisp_b200/csrc $(EXTRA)
 SRC       := qrisp_b200/csrc/qb2_api.cu qrisp_b200/csrc/qb2_pass.cu qrisp_b200/csrc/qb2_measure.cu
 OBJ       := $(SRC:.cu=.o)
 LIB       := qrisp_b200/lib/libqb2.so

@@ -140,6 +140,10 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_MAX_PHASES 8
 #define QB2_MAX_SMALL_BYTES 8192
 
+/* a pass that contains QB2_OP_MAT2/3/4 or the general QB2_OP_DIAG needs the full kernel; all
+ * other passes run a leaner one (smaller instruction footprint) */
+#define QB2_FEATURE_FULL 1u
+
 #define QB2_OP_MAT1 1 /* 2x2 on register bit b0 */
 #define QB2_OP_MAT2 2 /* 4x4 on register bits b0 < b1 (matrix index bit 0 <-> b0) */
 #define QB2_OP_MAT3 3 /* 8x8 on register bits 0,1,2 */
@@ -191,7 +195,8 @@ typedef struct qb2_pass_header { /* 128 bytes */
     uint32_t tabdesc_off; /* qb2_tab[] (inside the small section) */
     uint32_t tab_off;    /* phase tables, after the small section: uint32 (C64) / uint64 (C128) */
     uint32_t n_ops;
-    uint32_t rsv[2];
+    uint32_t features; /* QB2_FEATURE_*: which kernel variant the pass needs */
+    uint32_t rsv;
     qb2_seg seg[QB2_MAX_SEGS];
 } qb2_pass_header;
 

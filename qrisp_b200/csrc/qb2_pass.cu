@@ -18,6 +18,10 @@
 
 #include "qb2_internal.cuh"
 
+#ifndef QB2_MINB4
+#define QB2_MINB4 4
+#endif
+
 namespace qb2 {
 
 namespace {
@@ -146,6 +150,48 @@ __device__ __forceinline__ void st_stream(V *p, const V v) {
     __stcs(p, v);
 }
 
+// Coefficients of the op being executed: N reals from the device copy of the pass, fetched
+// with 16-byte loads from one address for the whole warp (a single sector per load) into
+// registers ONCE per op -- constant-bank reads indexed by a non-uniform register would be
+// re-issued for every register pair.
+template <typename real, int N>
+__device__ __forceinline__ void load_coefs(const real *__restrict__ g, real (&c)[N]) {
+    if constexpr (sizeof(real) == 4) {
+        static_for<0, N / 4>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
+            c[4 * i] = v.x;
+            c[4 * i + 1] = v.y;
+            c[4 * i + 2] = v.z;
+            c[4 * i + 3] = v.w;
+        });
+    } else {
+        static_for<0, N / 2>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(g) + i);
+            c[2 * i] = v.x;
+            c[2 * i + 1] = v.y;
+        });
+    }
+}
+
+template <typename real, int RB, int B>
+__device__ __forceinline__ void mat1_general(real (&re)[1 << RB], real (&im)[1 << RB], const real (&m)[8],
+                                             const uint32_t jmask) {
+    static_for<0, (1 << RB) / 2>([&](auto G) {
+        constexpr int g = decltype(G)::value;
+        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+        constexpr int j1 = j0 | (1 << B);
+        if ((jmask >> j0) & 1u) {
+            const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
+            re[j0] = fma(m[0], x0r, fma(-m[1], x0i, fma(m[2], x1r, -m[3] * x1i)));
+            im[j0] = fma(m[0], x0i, fma(m[1], x0r, fma(m[2], x1i, m[3] * x1r)));
+            re[j1] = fma(m[4], x0r, fma(-m[5], x0i, fma(m[6], x1r, -m[7] * x1i)));
+            im[j1] = fma(m[4], x0i, fma(m[5], x0r, fma(m[6], x1i, m[7] * x1r)));
+        }
+    });
+}
+
 struct PassParams {  // the small section of a pass, passed by value: lives in the constant bank
     uint4 q[QB2_MAX_SMALL_BYTES / 16];
 };
@@ -201,10 +247,13 @@ __device__ __forceinline__ void mat1_swap(real (&re)[1 << RB], real (&im)[1 << R
     });
 }
 
-template <typename real, int RB, int MAXT, int MINB>
+// FULL = false leaves out the rarely used op kinds (general per-amplitude DIAG, 4x4 / 8x8 /
+// 16x16 blocks): the common passes then run a kernel a third of the size, which matters
+// because the interpreter's working set of code competes for the instruction cache.
+template <typename real, int RB, int MAXT, int MINB, bool FULL>
 __global__ void __launch_bounds__(MAXT, MINB)
     pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
-                const uint64_t hi_base, const uint32_t ntiles, const uint32_t roots_off, const uint32_t ctx_off,
+                const real *__restrict__ gcoefs, const uint64_t hi_base, const uint32_t ntiles, const uint32_t roots_off, const uint32_t ctx_off,
                 const uint32_t tile_off, const __grid_constant__ PassParams P) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
@@ -274,7 +323,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
             const uint4 c = ctx[tid];
             xloc = tbase | ((uint64_t)c.y << 32 | c.x);
             const uint8_t *gb = state_b + xloc * sizeof(vec);
+#ifndef QB2_NOPIN
             asm volatile("" : "+l"(gb));  // keep base + uniform offset: two adds per address
+#endif
             const uint64_t *rp = a64 + ph.rphys;
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
@@ -359,7 +410,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                                       : __ldg(tables + tb[i].off + tab_index(tb[i], X) + tb[i].regoff);
                         w1 = unit_phase(s1, roots);
                     }
-                    const real *m = coefs + 2 * (size_t)op.data;
+                    const real *m = coefs + 2 * (size_t)op.data;  // convergent code: uniform constant reads
                     const real *v = m + 8;
                     const bool has_v = (fl & QB2_BFLY_V) != 0;
                     const bool is_real = (fl & QB2_BFLY_REAL) != 0;
@@ -460,7 +511,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                             re[j] = fma(xr_, wr, -xi_ * wi);
                             im[j] = fma(xr_, wi, xi_ * wr);
                         });
-                    } else {  // QB2_OP_DIAG: general, one table sum per amplitude
+                    } else if constexpr (FULL) {  // QB2_OP_DIAG: general, one table sum per amplitude
                         const frac *t0 = tables, *t1 = tables, *t2 = tables, *t3 = tables;
                         const uint16_t *g0 = a16, *g1 = a16, *g2 = a16, *g3 = a16;
                         t0 = tables + tb[0].off + tab_index(tb[0], X);
@@ -489,24 +540,33 @@ __global__ void __launch_bounds__(MAXT, MINB)
                             im[j] = fma(xr_, w.y, xi_ * w.x);
                         });
                     }
-                } else if (((X ^ op.cval) & op.cmask) == 0) {
-                    const real *m = coefs + 2 * (size_t)op.data;
+                } else {
+                  // The thread-level control below may diverge, and divergent code cannot use the
+                  // uniform datapath: read the 2x2 coefficients before it.
+                  const real *m = coefs + 2 * (size_t)op.data;
+                  real c8[8];
+                  if (kind == QB2_OP_MAT1) {
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) c8[k] = m[k];
+                  }
+                  if (((X ^ op.cval) & op.cmask) == 0) {
                     const uint32_t jmask = op.jmask;
                     const int b0 = op.b0, b1 = op.b1;
                     if (kind == QB2_OP_MAT1) {
                         const uint32_t shape = op.flags;
+
                         if (shape == QB2_MAT1_SWAP) {
                             static_for<0, RB>([&](auto B) {
                                 if (b0 == decltype(B)::value) mat1_swap<real, RB, decltype(B)::value>(re, im, jmask);
                             });
                         } else if (shape == QB2_MAT1_REAL) {
-                            const real a = m[0], b = m[2], c = m[4], d = m[6];
+                            const real a = c8[0], b = c8[2], c = c8[4], d = c8[6];
                             static_for<0, RB>([&](auto B) {
                                 if (b0 == decltype(B)::value)
                                     mat1_real<real, RB, decltype(B)::value>(re, im, a, b, c, d, jmask);
                             });
                         } else if (shape == QB2_MAT1_ANTI) {
-                            const real pr = m[2], pi = m[3], qr = m[4], qi = m[5];
+                            const real pr = c8[2], pi = c8[3], qr = c8[4], qi = c8[5];
                             static_for<0, RB>([&](auto B) {
                                 if (b0 == decltype(B)::value)
                                     mat1_anti<real, RB, decltype(B)::value>(re, im, pr, pi, qr, qi, jmask);
@@ -514,21 +574,24 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         } else {
                             static_for<0, RB>([&](auto B) {
                                 if (b0 == decltype(B)::value)
-                                    apply_mat<real, RB, 1, decltype(B)::value>(re, im, m, jmask);
+                                    mat1_general<real, RB, decltype(B)::value>(re, im, c8, jmask);
                             });
                         }
-                    } else if (kind == QB2_OP_MAT2) {
-                        static_for<0, RB>([&](auto B0) {
-                            static_for<decltype(B0)::value + 1, RB>([&](auto B1) {
-                                if (b0 == decltype(B0)::value && b1 == decltype(B1)::value)
-                                    apply_mat<real, RB, 2, decltype(B0)::value, decltype(B1)::value>(re, im, m, jmask);
+                    } else if constexpr (FULL) {
+                        if (kind == QB2_OP_MAT2) {
+                            static_for<0, RB>([&](auto B0) {
+                                static_for<decltype(B0)::value + 1, RB>([&](auto B1) {
+                                    if (b0 == decltype(B0)::value && b1 == decltype(B1)::value)
+                                        apply_mat<real, RB, 2, decltype(B0)::value, decltype(B1)::value>(re, im, m, jmask);
+                                });
                             });
-                        });
-                    } else if (kind == QB2_OP_MAT3) {
-                        if constexpr (RB >= 3) apply_mat<real, RB, 3, 0, 1, 2>(re, im, m, jmask);
-                    } else if (kind == QB2_OP_MAT4) {
-                        if constexpr (RB >= 4) apply_mat<real, RB, 4, 0, 1, 2, 3>(re, im, m, jmask);
+                        } else if (kind == QB2_OP_MAT3) {
+                            if constexpr (RB >= 3) apply_mat<real, RB, 3, 0, 1, 2>(re, im, m, jmask);
+                        } else if (kind == QB2_OP_MAT4) {
+                            if constexpr (RB >= 4) apply_mat<real, RB, 4, 0, 1, 2, 3>(re, im, m, jmask);
+                        }
                     }
+                  }
                 }
             }
         }
@@ -536,7 +599,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
         {
             const uint64_t *rp = a64 + phases[n_phases - 1].rphys;
             uint8_t *gb = reinterpret_cast<uint8_t *>(state) + xloc * sizeof(vec);
+#ifndef QB2_NOPIN
             asm volatile("" : "+l"(gb));
+#endif
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
                 vec v;
@@ -567,12 +632,12 @@ struct Variant {
     bool attr_set;
 };
 
-template <typename real, int RB, int MAXT, int MINB>
-int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
-                   cudaStream_t s) {
+template <typename real, int RB, int MAXT, int MINB, bool FULL>
+int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
+                  cudaStream_t s) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
-    auto kern = pass_kernel<real, RB, MAXT, MINB>;
+    auto kern = pass_kernel<real, RB, MAXT, MINB, FULL>;
     static bool attr_set = false;
     static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
     const uint32_t threads = 1u << (h->T - RB);
@@ -600,10 +665,19 @@ int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, cons
     static PassParams params;
     memcpy(&params, h, h->small_bytes);
     const frac *tables = reinterpret_cast<const frac *>(reinterpret_cast<const uint8_t *>(blob_dev) + h->tab_off);
-    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, hi_base, ntiles, roots_off, ctx_off, tile_off,
-                                     params);
+    const real *gcoefs = reinterpret_cast<const real *>(reinterpret_cast<const uint8_t *>(blob_dev) + h->coef_off);
+    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, gcoefs, hi_base, ntiles, roots_off, ctx_off,
+                                     tile_off, params);
     count_launch();
     return check_cuda(cudaGetLastError(), "pass_kernel launch");
+}
+
+template <typename real, int RB, int MAXT, int MINB>
+int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
+                   cudaStream_t s) {
+    // the host says which op kinds the pass contains (header.features)
+    if (h->features & QB2_FEATURE_FULL) return launch_kernel<real, RB, MAXT, MINB, true>(state, hi_base, h, blob_dev, ntiles, s);
+    return launch_kernel<real, RB, MAXT, MINB, false>(state, hi_base, h, blob_dev, ntiles, s);
 }
 
 }  // namespace
@@ -626,7 +700,7 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
     const uint32_t ntiles = 1u << (n - h->T);
     const int tb = h->T - h->r;
     if (dtype == QB2_C64) {
-        if (h->r == 4 && tb <= 8) return launch_variant<float, 4, 256, 4>(state, hi_base, h, blob_dev, ntiles, s);
+        if (h->r == 4 && tb <= 8) return launch_variant<float, 4, 256, QB2_MINB4>(state, hi_base, h, blob_dev, ntiles, s);
         if (h->r == 4 && tb == 9) return launch_variant<float, 4, 512, 2>(state, hi_base, h, blob_dev, ntiles, s);
         if (h->r == 5 && tb <= 8) return launch_variant<float, 5, 256, 2>(state, hi_base, h, blob_dev, ntiles, s);
         if (h->r == 3 && tb <= 8) return launch_variant<float, 3, 256, 6>(state, hi_base, h, blob_dev, ntiles, s);

@@ -509,6 +509,8 @@ class Planner:
         tab_off = align(small, 256)
         total = align(tab_off + n_tab_entries * np.dtype(frac_t).itemsize, 256)
 
+        # ops outside the lean kernel's repertoire (include/qrisp_b200.h QB2_FEATURE_FULL)
+        features = 1 if any(rec[24] in (2, 3, 4, OP_DIAG) for rec in ops_b) else 0
         blob = bytearray(total)
         hdr = struct.pack(
             "<IIIIBBBBIIIIIIIII2I",
@@ -529,7 +531,7 @@ class Planner:
             tabdesc_off,
             tab_off,
             len(ops_b),
-            0,
+            features,
             0,
         )
         assert len(hdr) == 64
