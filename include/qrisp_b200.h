@@ -143,6 +143,10 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 /* a pass that contains QB2_OP_MAT2/3/4 or the general QB2_OP_DIAG needs the full kernel; all
  * other passes run a leaner one (smaller instruction footprint) */
 #define QB2_FEATURE_FULL 1u
+/* phase 0 keeps tile positions 0..3 on thread bits 0..3 (one 128-byte line per 16 lanes) and the
+ * pass has the `pf` table: the kernel may fetch tiles with bulk async copies into shared
+ * memory, one tile ahead of the one being processed */
+#define QB2_FEATURE_PREFETCH 2u
 
 #define QB2_OP_MAT1 1 /* 2x2 on register bit b0 */
 #define QB2_OP_MAT2 2 /* 4x4 on register bits b0 < b1 (matrix index bit 0 <-> b0) */
@@ -163,7 +167,7 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
  * tables, b0=1 entries) evaluated once per thread, v[pair] = 2**(r-1) host-computed unit
  * factors that follow the 4 matrix coefficients at `data`.  Tables start at `tab`. */
 #define QB2_OP_BFLY 9
-#define QB2_BFLY_REAL 1 /* flags: the 2x2 block is real */
+#define QB2_BFLY_REAL 1 /* flags: the 2x2 block is real (always set: the kernel fuses real blocks only) */
 #define QB2_BFLY_V 2    /* flags: v[] present (else 1) */
 #define QB2_BFLY_W 4    /* flags: tables present (else w1 = 1) */
 
@@ -196,7 +200,9 @@ typedef struct qb2_pass_header { /* 128 bytes */
     uint32_t tab_off;    /* phase tables, after the small section: uint32 (C64) / uint64 (C128) */
     uint32_t n_ops;
     uint32_t features; /* QB2_FEATURE_*: which kernel variant the pass needs */
-    uint32_t rsv;
+    uint32_t pf;       /* QB2_FEATURE_PREFETCH: index into the u16 area of uint16[T-4]: for chunk bit i
+                          (tile position tile_pos[4+i]) the position (low byte) and its slot bit in the
+                          phase-0 layout of a tile buffer (high byte) */
     qb2_seg seg[QB2_MAX_SEGS];
 } qb2_pass_header;
 

@@ -13,6 +13,7 @@
 // the host so that both the store and the load side are bank-conflict free.
 //
 // HBM-bound by construction: algorithmic bytes per launch = 2 * 2**n * sizeof(amplitude).
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -141,6 +142,9 @@ __device__ __forceinline__ frac tab_mul(const qb2_tab &t, const uint64_t x) {
     return (frac)m.mult * (frac)v;
 }
 
+__device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
+
 template <typename V>
 __device__ __forceinline__ V ld_stream(const V *p) {
     return __ldcs(p);
@@ -191,6 +195,35 @@ __device__ __forceinline__ void mat1_general(real (&re)[1 << RB], real (&im)[1 <
         }
     });
 }
+
+// ---- mbarrier + 1-D bulk async copy (TMA) wrappers for the tile prefetch pipeline
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct PassParams {  // the small section of a pass, passed by value: lives in the constant bank
     uint4 q[QB2_MAX_SMALL_BYTES / 16];
@@ -250,7 +283,11 @@ __device__ __forceinline__ void mat1_swap(real (&re)[1 << RB], real (&im)[1 << R
 // FULL = false leaves out the rarely used op kinds (general per-amplitude DIAG, 4x4 / 8x8 /
 // 16x16 blocks): the common passes then run a kernel a third of the size, which matters
 // because the interpreter's working set of code competes for the instruction cache.
-template <typename real, int RB, int MAXT, int MINB, bool FULL>
+// PF = true: the next tile is fetched into shared memory by bulk async copies (TMA) while the
+// current one is processed, so that HBM latency overlaps the register work instead of adding
+// to it.  Two tile buffers; the buffer the current tile came from doubles as its exchange
+// scratch.  Needs the phase-0 distribution the planner marks with QB2_FEATURE_PREFETCH.
+template <typename real, int RB, int MAXT, int MINB, bool FULL, bool PF>
 __global__ void __launch_bounds__(MAXT, MINB)
     pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
                 const real *__restrict__ gcoefs, const uint64_t hi_base, const uint32_t ntiles, const uint32_t roots_off, const uint32_t ctx_off,
@@ -304,21 +341,73 @@ __global__ void __launch_bounds__(MAXT, MINB)
         ctx[p * nthreads + tid] =
             make_uint4((uint32_t)xt, (uint32_t)(xt >> 32), wb * (uint32_t)sizeof(vec), rb * (uint32_t)sizeof(vec));
     }
-    uint8_t *const tile_b = smem + tile_off;
+    uint8_t *tile_b = smem + tile_off;
     const uint8_t *const state_b = reinterpret_cast<const uint8_t *>(state);
+
+    auto tile_base = [&](uint32_t t) {
+        uint64_t tb = 0;
+        for (int s = 0; s < n_seg; ++s) {
+            const qb2_seg sg = H->seg[s];
+            tb |= (uint64_t)((t >> sg.src) & ((1u << sg.len) - 1u)) << sg.dst;
+        }
+        return tb;
+    };
+
+    // ---- prefetch pipeline state: thread c moves chunk c (16 amplitudes, one 128-byte line)
+    const uint32_t tile_bytes = (uint32_t)sizeof(vec) << H->T;
+    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + tile_off + 2 * tile_bytes);
+    uint64_t ch_goff = 0;  // physical offset of this thread's chunk inside a tile
+    uint32_t ch_soff = 0;  // byte offset of the chunk inside a tile buffer
+    auto prefetch = [&](uint32_t t, uint32_t which) {
+        if (tid == 0) mbar_expect_tx(&mbar[which], tile_bytes);
+        bulk_g2s(smem + tile_off + which * tile_bytes + ch_soff, state_b + (tile_base(t) | ch_goff) * sizeof(vec),
+                 16 * sizeof(vec), &mbar[which]);
+    };
+    if constexpr (PF) {
+        const uint16_t *pf = a16 + H->pf;
+        for (int i = 0; i < (int)H->T - 4; ++i)
+            if ((tid >> i) & 1u) {
+                ch_goff |= 1ull << (pf[i] & 0xffu);
+                ch_soff |= (uint32_t)sizeof(vec) << (pf[i] >> 8);
+            }
+        if (tid == 0) {
+            mbar_init(&mbar[0], 1);
+            mbar_init(&mbar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+    }
 
     real re[NR], im[NR];
 
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    uint32_t iter = 0;
+    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++iter) {
         // ---- physical offset of the tile (tile id bits deposited into the non-tile positions)
-        uint64_t tbase = 0;
-        for (int s = 0; s < n_seg; ++s) {
-            const qb2_seg sg = H->seg[s];
-            tbase |= (uint64_t)((t >> sg.src) & ((1u << sg.len) - 1u)) << sg.dst;
-        }
+        const uint64_t tbase = tile_base(t);
         // ---- phase 0: load
         uint64_t xloc;  // local physical index of this thread's register 0
-        {
+        if constexpr (PF) {
+            const uint32_t cur = iter & 1u;
+            const uint4 c = ctx[tid];
+            xloc = tbase | ((uint64_t)c.y << 32 | c.x);
+            tile_b = smem + tile_off + cur * tile_bytes;
+            mbar_wait(&mbar[cur], (iter >> 1) & 1u);
+            // phase-0 layout of the buffer: thread bit b = slot bit b, register j = slot j << TB
+            const uint8_t *rb0 = tile_b + tid * (uint32_t)sizeof(vec);
+            const uint32_t stride = (uint32_t)sizeof(vec) << TB;
+            static_for<0, NR>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                const vec v = *reinterpret_cast<const vec *>(rb0 + j * stride);
+                re[j] = v.x;
+                im[j] = v.y;
+            });
+            // everyone is done with both buffers (this one: just read; the other: last tile's
+            // exchange scratch): hand the other one to the async proxy for the next tile
+            fence_proxy_async();
+            __syncthreads();
+            if (t + gridDim.x < ntiles) prefetch(t + gridDim.x, cur ^ 1u);
+        } else {
             const qb2_phase &ph = phases[0];
             const uint4 c = ctx[tid];
             xloc = tbase | ((uint64_t)c.y << 32 | c.x);
@@ -362,7 +451,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         });
                     }
                 }
+#ifndef QB2_EXP_NOSYNC
                 __syncthreads();
+#endif
                 {
                     xloc = tbase | ((uint64_t)c.y << 32 | c.x);
                     const uint8_t *rp_ = tile_b + c.w;
@@ -385,7 +476,9 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         });
                     }
                 }
+#ifndef QB2_EXP_NOSYNC
                 __syncthreads();
+#endif
             }
             const uint64_t X = hi_base | xloc;
             // ---- ops of this phase, on registers
@@ -410,10 +503,12 @@ __global__ void __launch_bounds__(MAXT, MINB)
                                       : __ldg(tables + tb[i].off + tab_index(tb[i], X) + tb[i].regoff);
                         w1 = unit_phase(s1, roots);
                     }
-                    const real *m = coefs + 2 * (size_t)op.data;  // convergent code: uniform constant reads
+                    // REAL 2x2 block only (the planner fuses nothing else); the four entries are
+                    // read once, the pair factors v[] straight from the constant bank
+                    const real *m = coefs + 2 * (size_t)op.data;
                     const real *v = m + 8;
-                    const bool has_v = (fl & QB2_BFLY_V) != 0;
-                    const bool is_real = (fl & QB2_BFLY_REAL) != 0;
+                    real ma = m[0], mb = m[2], mc = m[4], md = m[6];
+                    opaque(ma), opaque(mb), opaque(mc), opaque(md);  // no re-reads inside the pair loop
                     const int b0 = op.b0;
                     static_for<0, RB>([&](auto B) {
                         constexpr int bb = decltype(B)::value;
@@ -423,24 +518,13 @@ __global__ void __launch_bounds__(MAXT, MINB)
                                 constexpr int j0 = ((g >> bb) << (bb + 1)) | (g & ((1 << bb) - 1));
                                 constexpr int j1 = j0 | (1 << bb);
                                 const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
-                                real tr, ti;
-                                if (is_real) {
-                                    re[j0] = fma(m[0], x0r, m[2] * x1r);
-                                    im[j0] = fma(m[0], x0i, m[2] * x1i);
-                                    tr = fma(m[4], x0r, m[6] * x1r);
-                                    ti = fma(m[4], x0i, m[6] * x1i);
-                                } else {
-                                    re[j0] = fma(m[0], x0r, fma(-m[1], x0i, fma(m[2], x1r, -m[3] * x1i)));
-                                    im[j0] = fma(m[0], x0i, fma(m[1], x0r, fma(m[2], x1i, m[3] * x1r)));
-                                    tr = fma(m[4], x0r, fma(-m[5], x0i, fma(m[6], x1r, -m[7] * x1i)));
-                                    ti = fma(m[4], x0i, fma(m[5], x0r, fma(m[6], x1i, m[7] * x1r)));
-                                }
-                                real cr = w1.x, ci = w1.y;
-                                if (has_v) {
-                                    const real vr = v[2 * g], vi = v[2 * g + 1];
-                                    cr = fma(w1.x, vr, -w1.y * vi);
-                                    ci = fma(w1.x, vi, w1.y * vr);
-                                }
+                                re[j0] = fma(ma, x0r, mb * x1r);
+                                im[j0] = fma(ma, x0i, mb * x1i);
+                                const real tr = fma(mc, x0r, md * x1r);
+                                const real ti = fma(mc, x0i, md * x1i);
+                                const real vr = v[2 * g], vi = v[2 * g + 1];
+                                const real cr = fma(w1.x, vr, -w1.y * vi);
+                                const real ci = fma(w1.x, vi, w1.y * vr);
                                 re[j1] = fma(tr, cr, -ti * ci);
                                 im[j1] = fma(tr, ci, ti * cr);
                             });
@@ -632,19 +716,21 @@ struct Variant {
     bool attr_set;
 };
 
-template <typename real, int RB, int MAXT, int MINB, bool FULL>
+template <typename real, int RB, int MAXT, int MINB, bool FULL, bool PF>
 int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
                   cudaStream_t s) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
-    auto kern = pass_kernel<real, RB, MAXT, MINB, FULL>;
+    auto kern = pass_kernel<real, RB, MAXT, MINB, FULL, PF>;
     static bool attr_set = false;
     static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
     const uint32_t threads = 1u << (h->T - RB);
     const uint32_t roots_off = 0;
     const uint32_t ctx_off = std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0;
     const uint32_t tile_off = ctx_off + h->n_phases * threads * 16u;
-    const size_t tile_bytes = h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0;
+    // PF: two tile buffers + two mbarriers; else one exchange buffer when there is an exchange
+    const size_t tile_bytes = PF ? 2 * ((size_t)sizeof(vec) << h->T) + 16
+                                 : (h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0);
     const size_t smem = tile_off + tile_bytes;
     if (!attr_set) {
         QB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -675,9 +761,19 @@ int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const
 template <typename real, int RB, int MAXT, int MINB>
 int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
                    cudaStream_t s) {
-    // the host says which op kinds the pass contains (header.features)
-    if (h->features & QB2_FEATURE_FULL) return launch_kernel<real, RB, MAXT, MINB, true>(state, hi_base, h, blob_dev, ntiles, s);
-    return launch_kernel<real, RB, MAXT, MINB, false>(state, hi_base, h, blob_dev, ntiles, s);
+    // the host says which op kinds the pass contains and whether its phase-0 distribution
+    // suits the prefetch pipeline (header.features)
+    static const bool no_pf = getenv("QB2_PREFETCH") == nullptr;  // experimental: slower than direct loads on B200
+    if constexpr (std::is_same<real, float>::value && RB == 4 && MAXT == 256) {
+        if ((h->features & QB2_FEATURE_PREFETCH) && h->T == 12 && !no_pf && ntiles >= 2) {
+            if (h->features & QB2_FEATURE_FULL)
+                return launch_kernel<real, RB, MAXT, 2, true, true>(state, hi_base, h, blob_dev, ntiles, s);
+            return launch_kernel<real, RB, MAXT, 3, false, true>(state, hi_base, h, blob_dev, ntiles, s);
+        }
+    }
+    if (h->features & QB2_FEATURE_FULL)
+        return launch_kernel<real, RB, MAXT, MINB, true, false>(state, hi_base, h, blob_dev, ntiles, s);
+    return launch_kernel<real, RB, MAXT, MINB, false, false>(state, hi_base, h, blob_dev, ntiles, s);
 }
 
 }  // namespace

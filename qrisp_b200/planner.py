@@ -406,7 +406,7 @@ class Planner:
                 m = _permute_matrix(mat, order)
                 sbits = sorted(bits)
                 i += 1
-                if k == 1 and not ctrls and cfg.fuse_bfly:
+                if k == 1 and not ctrls and cfg.fuse_bfly and np.max(np.abs(m.imag)) < 1e-16:
                     # butterfly: the phases that follow and vanish for b0=0 ride on the gate
                     terms, nxt = diag_run(i)
                     if terms:
@@ -468,6 +468,19 @@ class Planner:
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
+        # ---- prefetch table: where chunk bit i (tile position tile_pos[4+i]) lives in the phase-0
+        # layout of a tile buffer (thread bit b -> slot bit b, register bit i -> slot bit TB+i)
+        pf_feature, pf_index = 0, 0
+        R0 = phases[0][0]
+        TP0 = [x for x in tile_pos if x not in R0]
+        if T >= 8 and tile_pos[:4] == [0, 1, 2, 3] and TP0[:4] == [0, 1, 2, 3]:
+            entries = []
+            for x in tile_pos[4:]:
+                slot = TP0.index(x) if x in TP0 else TB + R0.index(x)
+                entries.append(x | (slot << 8))
+            pf_index = add16(entries)
+            pf_feature = 2
+
         # ---- segments: tile id bits -> non-tile local positions
         segs = []
         src = 0
@@ -511,6 +524,7 @@ class Planner:
 
         # ops outside the lean kernel's repertoire (include/qrisp_b200.h QB2_FEATURE_FULL)
         features = 1 if any(rec[24] in (2, 3, 4, OP_DIAG) for rec in ops_b) else 0
+        features |= pf_feature
         blob = bytearray(total)
         hdr = struct.pack(
             "<IIIIBBBBIIIIIIIII2I",
@@ -532,7 +546,7 @@ class Planner:
             tab_off,
             len(ops_b),
             features,
-            0,
+            pf_index,
         )
         assert len(hdr) == 64
         blob[0:64] = hdr
