@@ -306,7 +306,7 @@ def run_gpu_arm(args):
     peak, peak_src = measured_peaks()
     achieved = 2 * state_bytes / (pass_avg_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "pass_kernel<float,4,256,4>",
+        "kernel": "pass_kernel<float,RB=5,256 threads,2 CTAs/SM,lean>",
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
