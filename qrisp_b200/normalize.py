@@ -116,13 +116,42 @@ def diagonal_qubits(u, k):
     return [i for i in range(k) if not _bit(mixed, i)], [i for i in range(k) if _bit(mixed, i)]
 
 
+_TEMPLATES = {}  # (matrix bytes, k, max_targets, max_blocks, unit_tol) -> ops on qubits 0..k-1
+
+
 def normalize_instruction(matrix, qubits, max_targets=4, max_blocks=4, unit_tol=1e-6):
     """Classify one unitary instruction.  ``matrix`` is big endian in ``qubits``.
 
     Returns a list of normalised ops that, applied in order, equal the instruction.
     A dense block on more than ``max_targets`` qubits is returned as a :class:`CMat`
     all the same; the planner routes it to the big-matrix path.
+
+    Circuits repeat a handful of matrices thousands of times, so the classification is
+    memoised on the matrix bytes and re-targeted to the instruction's qubits.
     """
+    k = len(qubits)
+    if k <= 3:
+        u = np.ascontiguousarray(matrix, dtype=np.complex128)
+        key = (u.tobytes(), k, max_targets, max_blocks, unit_tol)
+        tmpl = _TEMPLATES.get(key)
+        if tmpl is None:
+            if len(_TEMPLATES) > 4096:
+                _TEMPLATES.clear()
+            tmpl = _normalize_instruction(u, tuple(range(k)), max_targets, max_blocks, unit_tol)
+            _TEMPLATES[key] = tmpl
+        out = []
+        for op in tmpl:
+            if op.kind == "relabel":
+                out.append(Relabel(qubits[op.a], qubits[op.b]))
+            elif op.kind == "diag":
+                out.append(DiagTerm([qubits[q] for q in op.qubits], op.turns))
+            else:
+                out.append(CMat([qubits[q] for q in op.targets], op.matrix, {qubits[q]: v for q, v in op.controls.items()}))
+        return out
+    return _normalize_instruction(matrix, qubits, max_targets, max_blocks, unit_tol)
+
+
+def _normalize_instruction(matrix, qubits, max_targets, max_blocks, unit_tol):
     k = len(qubits)
     u = np.asarray(matrix, dtype=np.complex128)
     q_le = tuple(qubits[::-1])  # index bit i <-> q_le[i]

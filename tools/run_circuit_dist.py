@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Time one synthetic circuit on a sharded state (torchrun, one rank per GPU):
+   python -m torch.distributed.run --nproc-per-node 8 ... tools/run_circuit_dist.py qft 36"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch, torch.distributed as dist
+from qrisp_b200.circuit import ghz_qft_circuit, random_circuit
+from qrisp_b200.distributed import ShardedStateVector
+
+kind, n = sys.argv[1], int(sys.argv[2])
+depth = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+lr = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+rank, world = dist.get_rank(), dist.get_world_size()
+qc = random_circuit(n, depth, seed=0) if kind == "random" else ghz_qft_circuit(n)
+instrs = [i for i in qc.data if i.matrix is not None]
+sv = ShardedStateVector(n)
+t0 = time.perf_counter()
+prog = sv.compile(instrs)
+t_plan = time.perf_counter() - t0
+res = []
+for rep in range(2):
+    sv.reset()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); prog.run(time_comm=(rep == 1)); e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res.append(float(t[0]))
+norm = sv.norm2()
+outs = sv.sample(16, list(range(n)), rng=np.random.default_rng(1))
+if rank == 0:
+    ms = res[-1]
+    print(json.dumps({"circuit": kind, "qubits": n, "gpus": world, "local_qubits": sv.n, "gates": len(instrs),
+                      "plan_s": round(t_plan, 3), "first_run_ms": round(res[0], 1), "sweep_ms": round(ms, 1),
+                      "comm_ms": round(prog.comm_ms, 1), "swaps": prog.n_swaps, "passes": prog.n_passes,
+                      "gates_per_s": round(len(instrs) / (ms * 1e-3), 1),
+                      "amp_updates_per_s": len(instrs) / (ms * 1e-3) * 2.0**n, "norm2": norm,
+                      "sample": [int(o) for o in outs[:4]]}))
+dist.destroy_process_group()
