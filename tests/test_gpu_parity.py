@@ -285,3 +285,38 @@ def test_multi_gpu_sharded_path():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "dist_gpu_check ok" in res.stdout
+
+
+def test_backend_object_and_apply_matrix(sim):
+    """The default-backend stand-in and the TensorFactor.apply_matrix stand-in."""
+    from qrisp_b200.engine import StateVector
+
+    qc = random_circuit(11, 4, seed=8)
+    qc.measure([0, 3, 10])
+    be = sim.B200Backend()
+    got = be.run(qc, None)
+    want = ref_sim.run(qc, None)
+    assert set(got) == set(want) and max(abs(got[k] - want[k]) for k in got) < ATOL64
+    sv = StateVector(6)
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    u, _ = np.linalg.qr(a)
+    sv.apply_matrix(u, (4, 1))
+    want = ref_sim.apply_matrix(ref_sim.zero_state(6), u, (4, 1), 6, threshold=False)
+    np.testing.assert_allclose(sv.statevector(), want, atol=ATOL64)
+
+
+def test_experimental_prefetch_path_matches(sim, monkeypatch):
+    """The TMA prefetch variant of the pass kernel (off by default) computes the same state."""
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); "
+        "from qrisp_b200.circuit import ghz_qft_circuit; from qrisp_b200.simulator import statevector_sim; "
+        "from oracle import ref_sim; qc = ghz_qft_circuit(20); "
+        "e = np.abs(statevector_sim(qc, T=12, r=4) - ref_sim.statevector(qc)).max(); print('ERR', e); assert e < 1e-5"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QB2_PREFETCH="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-1000:] + res.stderr[-2000:]

@@ -334,3 +334,63 @@ def test_no_cpu_fallback_without_device():
 
     with pytest.raises(_lib.Qb2Error):
         statevector_sim(ghz_qft_circuit(3))
+
+
+# ---------------------------------------------------------------------------------------
+# the Qrisp-facing adapter (duck typed: Qrisp itself is not importable on the GPU box)
+# ---------------------------------------------------------------------------------------
+
+
+class _FakeOp:
+    def __init__(self, name, matrix=None, params=()):
+        self.name, self._m, self.params = name, matrix, params
+
+    def get_unitary(self):
+        return self._m
+
+
+class _FakeInstr:
+    def __init__(self, op, qubits, clbits=()):
+        self.op, self.qubits, self.clbits = op, list(qubits), list(clbits)
+
+
+class _FakeQC:
+    """Looks like qrisp.QuantumCircuit as far as simulator.py:117-145 is concerned."""
+
+    def __init__(self, n, ncl):
+        self.qubits = [object() for _ in range(n)]
+        self.clbits = [object() for _ in range(ncl)]
+        self.data = []
+        self.transpiled = False
+
+    def transpile(self):
+        res = _FakeQC(0, 0)
+        res.qubits, res.clbits, res.data, res.transpiled = self.qubits, self.clbits, list(self.data), True
+        return res
+
+
+def test_from_qrisp_reads_the_fields_the_reference_reads():
+    from qrisp_b200 import circuit as C
+
+    qc = _FakeQC(3, 2)
+    q, c = qc.qubits, qc.clbits
+    qc.data.append(_FakeInstr(_FakeOp("qb_alloc"), [q[0]]))
+    qc.data.append(_FakeInstr(_FakeOp("h", C.GATE_H.astype(np.complex64)), [q[2]]))
+    qc.data.append(_FakeInstr(_FakeOp("cx", C._controlled(C.GATE_X)), [q[2], q[0]]))
+    qc.data.append(_FakeInstr(_FakeOp("p", C.p_matrix(0.25), params=(0.25,)), [q[1]]))
+    qc.data.append(_FakeInstr(_FakeOp("measure"), [q[0]], [c[1]]))
+    qc.data.append(_FakeInstr(_FakeOp("measure"), [q[2]], [c[0]]))
+    got = Circuit.from_qrisp(qc)
+    assert got.num_qubits == 3 and got.num_clbits == 2
+    assert [(i.name, i.qubits, i.clbits) for i in got.data] == [
+        ("qb_alloc", (0,), ()), ("h", (2,), ()), ("cx", (2, 0), ()), ("p", (1,), ()), ("measure", (0,), (1,)),
+        ("measure", (2,), (0,)),
+    ]
+    assert got.data[1].matrix.dtype == np.complex128 and got.data[3].params == (0.25,)
+    # the oracle on the converted circuit: Bell pair on qubits (2, 0), clbit 0 <- qubit 2
+    res = ref_sim.run(got, None)
+    assert set(res) == {"00", "11"}
+    with pytest.raises(NotImplementedError):
+        bad = _FakeQC(1, 1)
+        bad.data.append(_FakeInstr(_FakeOp("c_if_x", C.GATE_X), [bad.qubits[0]], [bad.clbits[0]]))
+        Circuit.from_qrisp(bad)
