@@ -305,3 +305,111 @@ def circuit_unitary(instrs, qubits):
         cols = instr.matrix @ cols.reshape(1 << kk, -1)
         u = np.moveaxis(cols.reshape(shape), list(range(kk)), loc).reshape(1 << k, 1 << k)
     return u
+
+
+# ------------------------------------------------------------------------------------
+# grouped application (what makes the reference fast on a CPU)
+# ------------------------------------------------------------------------------------
+
+
+def group_instructions(instrs, kmax=6):
+    """Greedy restatement of the EFFECT of the reference's ``group_qc``
+    (circuit_preprocessing.py:119-157): consecutive instructions are merged while their joint
+    support stays within ``kmax`` qubits; each group is applied as ONE dense unitary
+    (simulator.py:255 -> GroupedInstruction.get_instruction -> to_op().get_unitary()).  The
+    reference searches for the grouping with the best flop gain; the greedy rule below reaches
+    comparable group sizes on the benchmark circuits and is used for the CPU baseline only.
+    Returns a list of ``(qubits, unitary)``."""
+    groups = []
+    cur, qubits = [], []
+    for instr in instrs:
+        new = [q for q in instr.qubits if q not in qubits]
+        if cur and len(qubits) + len(new) > kmax:
+            groups.append((list(qubits), circuit_unitary(cur, qubits)))
+            cur, qubits = [], []
+            new = list(instr.qubits)
+        qubits.extend(new)
+        cur.append(instr)
+    if cur:
+        groups.append((list(qubits), circuit_unitary(cur, qubits)))
+    return groups
+
+
+def statevector_grouped(circuit, dtype=np.complex64, kmax=6):
+    """``statevector`` through :func:`group_instructions` (same result, fewer sweeps)."""
+    n = circuit.num_qubits
+    instrs = [i for i in circuit.data if i.matrix is not None]
+    psi = zero_state(n, dtype)
+    for qubits, u in group_instructions(instrs, kmax):
+        psi = apply_matrix(psi, u, qubits, n, threshold=False)
+    return psi
+
+
+# ------------------------------------------------------------------------------------
+# sparse application (the reference's SparseBiArray path)
+# ------------------------------------------------------------------------------------
+
+
+def _result_density(da, db, contraction):
+    """reference: bi_arrays.py:1197-1204 -- estimated density of a contraction result
+    (the reference calls the fraction of non-zeros ``sparsity``)."""
+    return 1.0 - (1.0 - da * db) ** contraction
+
+
+def apply_matrix_sparse(idx, val, matrix, qubits, n):
+    """``matrix`` applied to the sparse state ``(idx, val)`` (sorted basis indices, amplitudes).
+
+    Restates what the reference's sparse contraction computes (bi_arrays.py:415-520
+    ``SparseBiArray.contract`` via bi_array_helper's coordinate matching): amplitudes are
+    grouped by the index bits outside ``qubits``, every group is multiplied by ``matrix`` and
+    exact zeros of the product are dropped, so a diagonal gate keeps the support and a
+    Hadamard at most doubles it."""
+    k = len(qubits)
+    shifts = [n - 1 - q for q in qubits]  # qubit 0 is the most significant index bit
+    tmask = 0
+    for s in shifts:
+        tmask |= 1 << s
+    local = np.zeros(idx.shape, dtype=np.int64)
+    for i, s in enumerate(shifts):
+        local |= ((idx >> s) & 1) << (k - 1 - i)
+    groups, inv = np.unique(idx & ~tmask, return_inverse=True)
+    dense = np.zeros((1 << k, groups.size), dtype=val.dtype)
+    dense[local, inv] = val
+    out = np.asarray(matrix).astype(val.dtype) @ dense
+    rows, cols = np.nonzero(out)
+    new_idx = groups[cols]
+    for i, s in enumerate(shifts):
+        new_idx = new_idx | (((rows >> (k - 1 - i)) & 1) << s)
+    new_val = out[rows, cols]
+    order = np.argsort(new_idx, kind="stable")
+    return new_idx[order], new_val[order]
+
+
+def statevector_reference_path(circuit, dtype=np.complex64, kmax=6, sparsity_threshold=0.05):
+    """The statevector the way the reference reaches it FAST: grouped unitaries
+    (:func:`group_instructions`) applied to a state that starts sparse
+    (tensor_factor.py:40-50) and is contracted sparsely while the estimated density of the
+    result stays below ``contract_sparsity_threshold`` = 0.05 (tensor_factor.py:86-89,
+    bi_arrays.py:1197-1213), densely afterwards.  This is the CPU arm of ``bench.py``: on
+    GHZ-like inputs the sparse prefix is what keeps the reference's cost near O(2**n)."""
+    n = circuit.num_qubits
+    instrs = [i for i in circuit.data if i.matrix is not None]
+    idx = np.zeros(1, dtype=np.int64)
+    val = np.ones(1, dtype=dtype)
+    psi = None
+    size = float(1 << n)
+    for qubits, u in group_instructions(instrs, kmax):
+        if psi is None:
+            dm = np.count_nonzero(np.abs(u) > FLOAT_THRESH) / u.size
+            dense_next = _result_density(dm, idx.size / size, 1 << len(qubits)) > sparsity_threshold or size * u.size < 2**12
+            if dense_next:
+                psi = np.zeros(1 << n, dtype=dtype)
+                psi[idx] = val
+        if psi is None:
+            idx, val = apply_matrix_sparse(idx, val, u * (np.abs(u) > FLOAT_THRESH), qubits, n)
+        else:
+            psi = apply_matrix(psi, u, qubits, n, threshold=True)
+    if psi is None:
+        psi = np.zeros(1 << n, dtype=dtype)
+        psi[idx] = val
+    return psi

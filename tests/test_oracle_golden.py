@@ -52,6 +52,24 @@ def test_oracle_statevector_matches_reference(golden_dir, threshold):
         np.testing.assert_allclose(sv, g[case + "_sv"], atol=1e-5, err_msg=case)
 
 
+def test_oracle_reference_path_matches_reference(golden_dir):
+    """The CPU arm of bench.py (grouped unitaries, sparse while the state is sparse) reaches
+    the reference's statevectors too."""
+    g = load(golden_dir, "statevector.npz")
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        for kmax in (3, 6):
+            sv = ref_sim.statevector_reference_path(qc, dtype=np.complex128, kmax=kmax)
+            np.testing.assert_allclose(sv, g[case + "_sv"], atol=1e-5, err_msg=case)
+    # a state that stays sparse to the end (GHZ) and one that turns dense on the way
+    from qrisp_b200.circuit import ghz_qft_circuit
+
+    qc = ghz_qft_circuit(11)
+    np.testing.assert_allclose(ref_sim.statevector_reference_path(qc, dtype=np.complex128),
+                               ref_sim.statevector(qc, dtype=np.complex128), atol=1e-10)
+
+
 def _as_dict(keys, probs):
     return {str(k): float(p) for k, p in zip(keys, probs)}
 
