@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QB2_ABI_VERSION 4
+#define QB2_ABI_VERSION 5
 
 #define QB2_C64 0
 #define QB2_C128 1
@@ -139,6 +139,7 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_MAX_SEGS 16
 #define QB2_MAX_PHASES 8
 #define QB2_MAX_SMALL_BYTES 8192
+#define QB2_MAX_SLOTS 32
 
 /* a pass that contains QB2_OP_MAT2/3/4 or the general QB2_OP_DIAG needs the full kernel; all
  * other passes run a leaner one (smaller instruction footprint) */
@@ -170,6 +171,8 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_BFLY_REAL 1 /* flags: the 2x2 block is real (always set: the kernel fuses real blocks only) */
 #define QB2_BFLY_V 2    /* flags: v[] present (else 1) */
 #define QB2_BFLY_W 4    /* flags: tables present (else w1 = 1) */
+#define QB2_BFLY_VLOW 8 /* flags: v[pair] depends only on the register bits BELOW b0, i.e. on the low b0
+                           bits of the pair number: the kernel forms w1 * v for 2**b0 pairs only */
 
 /* qb2_op.flags of a QB2_OP_MAT1: the shape of the 2x2 block (all use the same 4 coefficients) */
 #define QB2_MAT1_GENERAL 0
@@ -177,6 +180,30 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_MAT1_ANTI 2 /* zero diagonal (X, Y and their phases) */
 #define QB2_MAT1_SWAP 3 /* exactly X: the two amplitudes trade places */
 
+/* qb2_op.code: derived from kind / b0 / b1 / flags / jmask by the host so that the kernel decodes an
+ * op with ONE jump (register indices must be compile-time constants, hence one arm per bit). */
+#define QB2_CODE_BFLY 0      /* + 4 * b0 + mode; mode 0: w only, 1: v only, 2: w * v[pair], 3: as 2 with VLOW */
+#define QB2_CODE_DIAG_THR 20
+#define QB2_CODE_DIAG_VEC 21
+#define QB2_CODE_DIAG_GEN 22
+#define QB2_CODE_DIAG_BIT 24 /* + 2 * b0 + (flags & 1) */
+#define QB2_CODE_MAT1 34     /* + 8 * b0 + 2 * shape + (jmask == all registers) */
+#define QB2_CODE_SWAPC 74    /* + 5 * b0 + c: X on register bit b0 controlled by register bit c */
+#define QB2_CODE_MAT2 99     /* + index of (b0, b1) in (0,1),(0,2),(0,3),(0,4),(1,2),...,(3,4) */
+#define QB2_CODE_MAT3 109
+#define QB2_CODE_MAT4 110
+/* Fixed block right after the header: byte offset (from the thread's base address) of register j at
+ * the load of a tile (first phase's distribution) and at its store, and the physical offset
+ * (amplitudes) of thread bit b at the store.  The store may RELABEL tile positions: when the last
+ * phase holds the lowest positions in registers, the host swaps them with the positions on the lane
+ * bits, so that the store still writes whole 128-byte lines without another exchange; the host's
+ * qubit map follows (this replaces the reference's data-moving TensorFactor.swap, tensor_factor.py:55-65). */
+#define QB2_IO_OFFSET 128
+typedef struct qb2_io {
+    uint64_t load_off[32];
+    uint64_t store_off[32];
+    uint64_t store_col[16];
+} qb2_io;
 typedef struct qb2_seg { /* tile id bits [src, src+len) go to physical bits [dst, dst+len) */
     uint8_t src, dst, len, rsv;
 } qb2_seg;
@@ -200,9 +227,9 @@ typedef struct qb2_pass_header { /* 128 bytes */
     uint32_t tab_off;    /* phase tables, after the small section: uint32 (C64) / uint64 (C128) */
     uint32_t n_ops;
     uint32_t features; /* QB2_FEATURE_*: which kernel variant the pass needs */
-    uint32_t pf;       /* QB2_FEATURE_PREFETCH: index into the u16 area of uint16[T-4]: for chunk bit i
-                          (tile position tile_pos[4+i]) the position (low byte) and its slot bit in the
-                          phase-0 layout of a tile buffer (high byte) */
+    uint16_t pf;       /* QB2_FEATURE_PREFETCH: index into the u16 area of uint16[T-4] (complex128: T-3): the
+                          physical position of every 128-byte-line index bit of a tile */
+    uint16_t n_slots;  /* phase slots used by the pass (see qb2_op.b1), at most QB2_MAX_SLOTS */
     qb2_seg seg[QB2_MAX_SEGS];
 } qb2_pass_header;
 
@@ -227,11 +254,20 @@ typedef struct qb2_op { /* 32 bytes */
     uint64_t cmask; /* controls over the physical index, register positions excluded */
     uint64_t cval;
     uint32_t jmask; /* bit j set: register j satisfies the register-position controls */
-    uint32_t data;  /* MAT: first coefficient (complex elements from coef_off, row-major);
+    uint16_t data;  /* MAT: first coefficient (complex elements from coef_off, row-major);
                        DIAG: first table descriptor (index from tabdesc_off) */
+    uint16_t code;  /* QB2_CODE_*: kind x register bit x variant, the one number the kernel switches on */
     uint8_t kind;
     uint8_t b0;
-    uint8_t b1;
+    uint8_t b1;       /* MAT2: second register bit.  MAT1 with shape SWAP: 1 + c when the only register-bit
+                         control is register bit c = 1 (jmask = registers with bit c set), else 0.
+                         BFLY / DIAG_THR / DIAG_BIT: 1 + phase slot, or 0.  A slot is given to an op whose
+                         descriptors are all multiplier ladders (qb2_mul): such a phase is LINEAR in the
+                         index bits, so it splits into a part that depends on the thread (computed once per
+                         CTA, kept in shared memory) and a part that depends on the tile (computed once per
+                         tile by one thread per slot); executing the op then costs two shared-memory reads
+                         instead of a walk over the descriptors.  A DIAG_BIT whose b0=0 phase is live
+                         (flags & 1 clear) owns two consecutive slots: thread-only ladders, then all. */
     uint8_t ntab_thr; /* DIAG: tables that depend on thread/tile bits only (come first) */
     uint8_t ntab_reg; /* DIAG: tables that also depend on register bits */
     uint8_t flags;

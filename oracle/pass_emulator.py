@@ -28,17 +28,28 @@ class ParsedPass:
 def parse(blob):
     b = bytes(blob)
     (magic, total, small, n, T, r, dtype, n_seg, n_phases, phases_off, ops_off, coef_off, u16_off, u64_off,
-     tabdesc_off, tab_off, n_ops, _, _) = struct.unpack_from("<IIIIBBBBIIIIIIIII2I", b, 0)
+     tabdesc_off, tab_off, n_ops, _features, _pf, n_slots) = struct.unpack_from("<IIIIBBBBIIIIIIIIIIHH", b, 0)
     assert magic == MAGIC and total == len(b), (hex(magic), total, len(b))
     P = ParsedPass()
-    P.n, P.T, P.r, P.dtype, P.small = n, T, r, dtype, small
+    P.n, P.T, P.r, P.dtype, P.small, P.n_slots = n, T, r, dtype, small, n_slots
     P.segs = [struct.unpack_from("<BBBB", b, 64 + 4 * i)[:3] for i in range(n_seg)]
     P.phases = [struct.unpack_from("<8I", b, phases_off + 32 * i)[:7] for i in range(n_phases)]
     P.ops = []
     for i in range(n_ops):
-        cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags, tab = struct.unpack_from("<QQIIBBBBBBH", b, ops_off + 32 * i)
-        P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, kind=kind, b0=b0, b1=b1, nthr=nthr, nreg=nreg,
-                          flags=flags, tab=tab))
+        cmask, cval, jmask, data, code, kind, b0, b1, nthr, nreg, flags, tab = struct.unpack_from(
+            "<QQIHHBBBBBBH", b, ops_off + 32 * i)
+        P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, code=code, kind=kind, b0=b0, b1=b1, nthr=nthr,
+                          nreg=nreg, flags=flags, tab=tab))
+        assert code == _expected_code(P.ops[-1], 1 << r), (code, P.ops[-1])
+    P.io = np.frombuffer(b, dtype=np.uint64, count=80, offset=128)
+    # phase slots: every slotted op owns its own slot(s) inside [0, n_slots)
+    used = []
+    for op in P.ops:
+        if op["kind"] in (6, 7, 9) and op["b1"]:
+            need = 2 if op["kind"] == 7 and not op["flags"] & 1 else 1
+            used.extend(range(op["b1"] - 1, op["b1"] - 1 + need))
+    assert sorted(used) == list(range(n_slots)), (used, n_slots)
+    assert n_slots <= 32
     real_t = np.float32 if dtype == 0 else np.float64
     frac_t = np.uint32 if dtype == 0 else np.uint64
     P.real_t, P.frac_t = real_t, frac_t
@@ -57,6 +68,26 @@ def parse(blob):
     P.a16 = np.frombuffer(b, dtype=np.uint16, count=(small - u16_off) // 2, offset=u16_off)
     P.tables = np.frombuffer(b, dtype=frac_t, count=(total - tab_off) // np.dtype(frac_t).itemsize, offset=tab_off)
     return P
+
+
+def _expected_code(op, NR):
+    """qb2_op.code as the header defines it (QB2_CODE_*), recomputed from the other fields."""
+    kind, b0, b1, fl = op["kind"], op["b0"], op["b1"], op["flags"]
+    if kind == 9:
+        mode = 0 if not fl & 2 else (1 if not fl & 4 else (3 if fl & 8 else 2))
+        return 4 * b0 + mode
+    if kind in (6, 8, 5):
+        return {6: 20, 8: 21, 5: 22}[kind]
+    if kind == 7:
+        return 24 + 2 * b0 + (fl & 1)
+    if kind == 1:
+        if fl == 3 and b1:
+            return 74 + 5 * b0 + (b1 - 1)
+        return 34 + 8 * b0 + 2 * fl + (1 if op["jmask"] == (1 << NR) - 1 else 0)
+    if kind == 2:
+        pairs = [(a, c) for a in range(5) for c in range(a + 1, 5)]
+        return 99 + pairs.index((b0, b1))
+    return 109 if kind == 3 else 110
 
 
 def _tab_index(tab, X):
@@ -120,7 +151,10 @@ def run(blob, state, hi_base=0, report=None):
         assert len(P.phases) <= 8
         xloc = np.uint64(tbase) | thread_cols(ph0[2], P.a64, False)
         rp = P.a64[ph0[3] : ph0[3] + NR]
-        addr = xloc[:, None] | rp[None, :]
+        csize = 8 if P.dtype == 0 else 16
+        assert np.array_equal(P.io[:NR], rp * np.uint64(csize)), "qb2_io.load_off"
+        addr = xloc[:, None] | (P.io[:NR] // np.uint64(csize))[None, :]
+        load_addr = addr.astype(np.int64)
         regs = state[addr.astype(np.int64)]  # [thread, j]
         seen = np.zeros(1 << T, dtype=bool)
         for pi, (first_op, nops, pcol, rphys, xw, xr, xflags) in enumerate(P.phases):
@@ -152,6 +186,21 @@ def run(blob, state, hi_base=0, report=None):
             X = np.uint64(hi_base) | xloc
             for o in range(first_op, first_op + nops):
                 op = P.ops[o]
+                if op["kind"] in (6, 7, 9) and op["b1"]:
+                    # phase slot: the kernel evaluates the op's ladders separately on the thread's
+                    # part of the index (once per CTA) and on the tile's part (once per tile) and adds
+                    # the two -- check that this is what the ladders evaluate to on the whole index
+                    assert op["b1"] <= P.n_slots
+                    first = op["tab"] if op["kind"] == 9 else op["data"]
+                    descs = P.tabs[first : first + op["nthr"] + op["nreg"]]
+                    assert descs and all("mul" in d for d in descs), "a slot needs multiplier ladders only"
+                    x_thr = np.uint64(hi_base) | (xloc & ~np.uint64(tbase))
+                    x_tile = np.full(nthreads, np.uint64(tbase), dtype=np.uint64)
+                    for d in descs:
+                        whole = _mul_phase(d, X, P.frac_t)
+                        with np.errstate(over="ignore"):
+                            split = (_mul_phase(d, x_thr, P.frac_t) + _mul_phase(d, x_tile, P.frac_t)).astype(P.frac_t)
+                        assert np.array_equal(whole, split), "ladder is not additive over thread / tile bits"
                 if op["kind"] == 9:  # BFLY
                     b0, fl = op["b0"], op["flags"]
                     cf = P.coefs[2 * op["data"] : 2 * op["data"] + 8 + NR].astype(np.float64)
@@ -173,7 +222,9 @@ def run(blob, state, hi_base=0, report=None):
                         j0 = ((g >> b0) << (b0 + 1)) | (g & ((1 << b0) - 1))
                         j1 = j0 | (1 << b0)
                         x0, x1 = regs[:, j0].astype(np.complex128), regs[:, j1].astype(np.complex128)
-                        c = w1 * (v[g] if fl & 2 else 1.0)
+                        # QB2_BFLY_VLOW (8): the kernel reads v[] for the low b0 bits of the pair only
+                        gv = g & ((1 << b0) - 1) if fl & 8 else g
+                        c = w1 * (v[gv] if fl & 2 else 1.0)
                         new[:, j0] = (m[0, 0] * x0 + m[0, 1] * x1).astype(cdt)
                         new[:, j1] = ((m[1, 0] * x0 + m[1, 1] * x1) * c).astype(cdt)
                     regs = new
@@ -230,18 +281,31 @@ def run(blob, state, hi_base=0, report=None):
                             m = np.array([[0, 1], [1, 0]], dtype=np.complex128)
                     on = ((X ^ np.uint64(op["cval"])) & np.uint64(op["cmask"])) == 0
                     tmask = sum(1 << bb for bb in bits)
+                    jmask = op["jmask"]
+                    if k == 1 and op["flags"] == 3 and op["b1"]:
+                        # CX inside the registers: the kernel ignores jmask and swaps the pairs whose
+                        # register bit b1-1 is set
+                        cb = op["b1"] - 1
+                        assert cb != op["b0"] and cb < r
+                        jmask = sum(1 << j for j in range(NR) if (j >> cb) & 1)
                     new = regs.copy()
                     for base in range(NR):
-                        if base & tmask or not (op["jmask"] >> base) & 1:
+                        if base & tmask or not (jmask >> base) & 1:
                             continue
                         js = [base | sum(((c >> i) & 1) << bits[i] for i in range(k)) for c in range(D)]
                         x = regs[:, js].astype(np.complex128)
                         y = x @ m.T
                         new[np.ix_(on, js)] = y[on].astype(cdt)
                     regs = new
-        last = P.phases[-1]
-        rp = P.a64[last[3] : last[3] + NR]
-        addr = (xloc[:, None] | rp[None, :]).astype(np.int64)
+        # store: qb2_io.store_col / store_off (the tile may be stored relabelled; then the columns
+        # differ from the last phase's own, but they must still cover the tile exactly once)
+        sloc = np.full(nthreads, np.uint64(tbase), dtype=np.uint64)
+        for bb in range(TB):
+            sel = ((tid >> np.uint64(bb)) & np.uint64(1)).astype(bool)
+            sloc[sel] |= P.io[64 + bb]
+        addr = (sloc[:, None] | (P.io[32 : 32 + NR] // np.uint64(csize))[None, :]).astype(np.int64)
+        assert len(np.unique(addr)) == addr.size, "store addresses collide"
+        assert np.array_equal(np.sort(addr.reshape(-1)), np.sort(load_addr.reshape(-1))), "store leaves the tile"
         state[addr] = regs
     return state
 

@@ -15,12 +15,14 @@ template <>
 struct Traits<float> {
     using vec = float2;
     using frac = uint32_t;
+    using frac2 = uint2;
     static constexpr int dtype = QB2_C64;
 };
 template <>
 struct Traits<double> {
     using vec = double2;
     using frac = uint64_t;
+    using frac2 = ulonglong2;
     static constexpr int dtype = QB2_C128;
 };
 

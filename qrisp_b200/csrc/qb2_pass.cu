@@ -12,6 +12,11 @@
 // become register bits; its slot map is an XOR-linear function of the thread id chosen by
 // the host so that both the store and the load side are bank-conflict free.
 //
+// complex64 arithmetic runs on Blackwell's packed FP32 pipe: an amplitude is one 64-bit
+// register pair (re, im) from the load to the store, and every operation is an FADD2 / FMUL2 /
+// FFMA2 on the pair.  A complex multiplication is two instructions (the operand swizzles
+// .LO_HI / scalar splat / per-half negation are free), a real butterfly is two.
+//
 // HBM-bound by construction: algorithmic bytes per launch = 2 * 2**n * sizeof(amplitude).
 #include <cstdlib>
 #include <cstring>
@@ -30,11 +35,62 @@ namespace {
 constexpr int ROOT_BITS = 8;
 constexpr int NROOT = 1 << ROOT_BITS;
 
+// ---- complex arithmetic on one amplitude
+template <typename real>
+struct Cx;
+template <>
+struct Cx<float> {
+    using amp = float2;
+    static __device__ __forceinline__ amp add(amp a, amp b) { return __fadd2_rn(a, b); }
+    static __device__ __forceinline__ amp sub(amp a, amp b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+    static __device__ __forceinline__ amp rmul(amp a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+    static __device__ __forceinline__ amp rfma(amp a, float s, amp c) { return __ffma2_rn(a, make_float2(s, s), c); }
+    // a * (cr + i ci): FMUL2 a, cr.splat ; FFMA2 a.LO_HI, (-ci, ci), t
+    static __device__ __forceinline__ amp cmul(amp a, float cr, float ci) {
+        return __ffma2_rn(make_float2(a.y, a.x), make_float2(-ci, ci), __fmul2_rn(a, make_float2(cr, cr)));
+    }
+    static __device__ __forceinline__ amp cfma(amp a, float cr, float ci, amp acc) {
+        return __ffma2_rn(make_float2(a.y, a.x), make_float2(-ci, ci), __ffma2_rn(a, make_float2(cr, cr), acc));
+    }
+};
+template <>
+struct Cx<double> {
+    using amp = double2;
+    static __device__ __forceinline__ amp add(amp a, amp b) { return make_double2(a.x + b.x, a.y + b.y); }
+    static __device__ __forceinline__ amp sub(amp a, amp b) { return make_double2(a.x - b.x, a.y - b.y); }
+    static __device__ __forceinline__ amp rmul(amp a, double s) { return make_double2(a.x * s, a.y * s); }
+    static __device__ __forceinline__ amp rfma(amp a, double s, amp c) { return make_double2(fma(a.x, s, c.x), fma(a.y, s, c.y)); }
+    static __device__ __forceinline__ amp cmul(amp a, double cr, double ci) {
+        return make_double2(fma(a.x, cr, -a.y * ci), fma(a.x, ci, a.y * cr));
+    }
+    static __device__ __forceinline__ amp cfma(amp a, double cr, double ci, amp acc) {
+        return make_double2(fma(a.x, cr, fma(-a.y, ci, acc.x)), fma(a.x, ci, fma(a.y, cr, acc.y)));
+    }
+};
+
 template <int I, int N, typename F>
 __device__ __forceinline__ void static_for(F &&f) {
     if constexpr (I < N) {
         f(std::integral_constant<int, I>{});
         static_for<I + 1, N>(f);
+    }
+}
+
+// run f(integral_constant<int, v>) for a runtime v in [0, N): a switch, so that the compiler sees
+// mutually exclusive arms (a chain of ifs gets if-converted into register copies)
+template <int N, typename F>
+__device__ __forceinline__ void dispatch(const int v, F &&f) {
+    static_assert(N <= 8, "dispatch: at most 8 arms");
+    switch (v) {
+        case 0: if constexpr (N > 0) f(std::integral_constant<int, 0>{}); break;
+        case 1: if constexpr (N > 1) f(std::integral_constant<int, 1>{}); break;
+        case 2: if constexpr (N > 2) f(std::integral_constant<int, 2>{}); break;
+        case 3: if constexpr (N > 3) f(std::integral_constant<int, 3>{}); break;
+        case 4: if constexpr (N > 4) f(std::integral_constant<int, 4>{}); break;
+        case 5: if constexpr (N > 5) f(std::integral_constant<int, 5>{}); break;
+        case 6: if constexpr (N > 6) f(std::integral_constant<int, 6>{}); break;
+        case 7: if constexpr (N > 7) f(std::integral_constant<int, 7>{}); break;
+        default: break;
     }
 }
 
@@ -66,35 +122,26 @@ struct BitMap {
 };
 
 template <typename real, int RB, int K, int P0, int P1 = -1, int P2 = -1, int P3 = -1>
-__device__ __forceinline__ void apply_mat(real (&re)[1 << RB], real (&im)[1 << RB], const real *__restrict__ m,
+__device__ __forceinline__ void apply_mat(typename Cx<real>::amp (&a)[1 << RB], const real *__restrict__ m,
                                           const uint32_t jmask) {
     using BM = BitMap<RB, K, P0, P1, P2, P3>;
+    using C = Cx<real>;
+    using amp = typename C::amp;
     constexpr int D = 1 << K;
     constexpr int NG = (1 << RB) / D;
     static_for<0, NG>([&](auto G) {
         constexpr int base = BM::base(decltype(G)::value);
         if ((jmask >> base) & 1u) {
-            real xr[D], xi[D];
-            static_for<0, D>([&](auto C) {
-                constexpr int j = base | BM::dep(decltype(C)::value);
-                xr[decltype(C)::value] = re[j];
-                xi[decltype(C)::value] = im[j];
-            });
+            amp x[D];
+            static_for<0, D>([&](auto Cc) { x[decltype(Cc)::value] = a[base | BM::dep(decltype(Cc)::value)]; });
             static_for<0, D>([&](auto Rw) {
                 constexpr int row = decltype(Rw)::value;
-                real ar = 0, ai = 0;
-                static_for<0, D>([&](auto C) {
-                    constexpr int col = decltype(C)::value;
-                    const real mr = m[2 * (row * D + col)];
-                    const real mi = m[2 * (row * D + col) + 1];
-                    ar = fma(mr, xr[col], ar);
-                    ar = fma(-mi, xi[col], ar);
-                    ai = fma(mr, xi[col], ai);
-                    ai = fma(mi, xr[col], ai);
+                amp acc = C::cmul(x[0], m[2 * (row * D)], m[2 * (row * D) + 1]);
+                static_for<1, D>([&](auto Cc) {
+                    constexpr int col = decltype(Cc)::value;
+                    acc = C::cfma(x[col], m[2 * (row * D + col)], m[2 * (row * D + col) + 1], acc);
                 });
-                constexpr int j = base | BM::dep(row);
-                re[j] = ar;
-                im[j] = ai;
+                a[base | BM::dep(row)] = acc;
             });
         }
     });
@@ -154,151 +201,150 @@ __device__ __forceinline__ void st_stream(V *p, const V v) {
     __stcs(p, v);
 }
 
-// Coefficients of the op being executed: N reals from the device copy of the pass, fetched
-// with 16-byte loads from one address for the whole warp (a single sector per load) into
-// registers ONCE per op -- constant-bank reads indexed by a non-uniform register would be
-// re-issued for every register pair.
-template <typename real, int N>
-__device__ __forceinline__ void load_coefs(const real *__restrict__ g, real (&c)[N]) {
-    if constexpr (sizeof(real) == 4) {
-        static_for<0, N / 4>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + i);
-            c[4 * i] = v.x;
-            c[4 * i + 1] = v.y;
-            c[4 * i + 2] = v.z;
-            c[4 * i + 3] = v.w;
-        });
-    } else {
-        static_for<0, N / 2>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            const double2 v = __ldg(reinterpret_cast<const double2 *>(g) + i);
-            c[2 * i] = v.x;
-            c[2 * i + 1] = v.y;
-        });
-    }
-}
-
-template <typename real, int RB, int B>
-__device__ __forceinline__ void mat1_general(real (&re)[1 << RB], real (&im)[1 << RB], const real (&m)[8],
-                                             const uint32_t jmask) {
-    static_for<0, (1 << RB) / 2>([&](auto G) {
-        constexpr int g = decltype(G)::value;
-        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
-        constexpr int j1 = j0 | (1 << B);
-        if ((jmask >> j0) & 1u) {
-            const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
-            re[j0] = fma(m[0], x0r, fma(-m[1], x0i, fma(m[2], x1r, -m[3] * x1i)));
-            im[j0] = fma(m[0], x0i, fma(m[1], x0r, fma(m[2], x1i, m[3] * x1r)));
-            re[j1] = fma(m[4], x0r, fma(-m[5], x0i, fma(m[6], x1r, -m[7] * x1i)));
-            im[j1] = fma(m[4], x0i, fma(m[5], x0r, fma(m[6], x1i, m[7] * x1r)));
-        }
-    });
-}
-
-// ---- mbarrier + 1-D bulk async copy (TMA) wrappers for the tile prefetch pipeline
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 struct PassParams {  // the small section of a pass, passed by value: lives in the constant bank
     uint4 q[QB2_MAX_SMALL_BYTES / 16];
 };
 
-template <typename real, int RB, int B>
-__device__ __forceinline__ void mat1_real(real (&re)[1 << RB], real (&im)[1 << RB], const real a, const real b,
-                                          const real c, const real d, const uint32_t jmask) {
+// pair g of a gate on register bit B: j0 has bit B clear, j1 = j0 | 1 << B
+template <int B>
+__host__ __device__ constexpr int pair_j0(int g) {
+    return ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
+}
+
+// ---- 2x2 gates on register bit B.  ALLJ: every pair takes part (no register-bit controls).
+template <typename real, int RB, int B, bool ALLJ>
+__device__ __forceinline__ void mat1_general(typename Cx<real>::amp (&a)[1 << RB], const real (&m)[8], const uint32_t jmask) {
+    using C = Cx<real>;
     static_for<0, (1 << RB) / 2>([&](auto G) {
-        constexpr int g = decltype(G)::value;
-        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
-        constexpr int j1 = j0 | (1 << B);
-        if ((jmask >> j0) & 1u) {
-            const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
-            re[j0] = fma(a, x0r, b * x1r);
-            im[j0] = fma(a, x0i, b * x1i);
-            re[j1] = fma(c, x0r, d * x1r);
-            im[j1] = fma(c, x0i, d * x1i);
+        constexpr int j0 = pair_j0<B>(decltype(G)::value), j1 = j0 | (1 << B);
+        if (ALLJ || ((jmask >> j0) & 1u)) {
+            const auto x0 = a[j0], x1 = a[j1];
+            a[j0] = C::cfma(x1, m[2], m[3], C::cmul(x0, m[0], m[1]));
+            a[j1] = C::cfma(x1, m[6], m[7], C::cmul(x0, m[4], m[5]));
+        }
+    });
+}
+
+template <typename real, int RB, int B, bool ALLJ>
+__device__ __forceinline__ void mat1_real(typename Cx<real>::amp (&a)[1 << RB], const real (&m)[8], const uint32_t jmask) {
+    using C = Cx<real>;
+    static_for<0, (1 << RB) / 2>([&](auto G) {
+        constexpr int j0 = pair_j0<B>(decltype(G)::value), j1 = j0 | (1 << B);
+        if (ALLJ || ((jmask >> j0) & 1u)) {
+            const auto x0 = a[j0], x1 = a[j1];
+            a[j0] = C::rfma(x1, m[2], C::rmul(x0, m[0]));
+            a[j1] = C::rfma(x1, m[6], C::rmul(x0, m[4]));
         }
     });
 }
 
 // anti-diagonal 2x2: new0 = p * x1, new1 = q * x0
-template <typename real, int RB, int B>
-__device__ __forceinline__ void mat1_anti(real (&re)[1 << RB], real (&im)[1 << RB], const real pr, const real pi,
-                                          const real qr, const real qi, const uint32_t jmask) {
+template <typename real, int RB, int B, bool ALLJ>
+__device__ __forceinline__ void mat1_anti(typename Cx<real>::amp (&a)[1 << RB], const real (&m)[8], const uint32_t jmask) {
+    using C = Cx<real>;
     static_for<0, (1 << RB) / 2>([&](auto G) {
-        constexpr int g = decltype(G)::value;
-        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
-        constexpr int j1 = j0 | (1 << B);
-        if ((jmask >> j0) & 1u) {
-            const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
-            re[j0] = fma(pr, x1r, -pi * x1i);
-            im[j0] = fma(pr, x1i, pi * x1r);
-            re[j1] = fma(qr, x0r, -qi * x0i);
-            im[j1] = fma(qr, x0i, qi * x0r);
+        constexpr int j0 = pair_j0<B>(decltype(G)::value), j1 = j0 | (1 << B);
+        if (ALLJ || ((jmask >> j0) & 1u)) {
+            const auto x0 = a[j0], x1 = a[j1];
+            a[j0] = C::cmul(x1, m[2], m[3]);
+            a[j1] = C::cmul(x0, m[4], m[5]);
         }
     });
 }
 
-template <typename real, int RB, int B>
-__device__ __forceinline__ void mat1_swap(real (&re)[1 << RB], real (&im)[1 << RB], const uint32_t jmask) {
+// Register swaps are written as XOR swaps on the raw words: with plain copies the compiler
+// renames registers inside every arm of the bit dispatch and then copies the WHOLE register
+// array at the join (about a thousand MOVs plus spills for the 20 CX arms).
+__device__ __forceinline__ void xor_swap(float2 &p, float2 &q, const uint32_t mask) {
+    uint32_t px = __float_as_uint(p.x), py = __float_as_uint(p.y), qx = __float_as_uint(q.x), qy = __float_as_uint(q.y);
+    const uint32_t tx = (px ^ qx) & mask, ty = (py ^ qy) & mask;
+    px ^= tx, qx ^= tx, py ^= ty, qy ^= ty;
+    p = make_float2(__uint_as_float(px), __uint_as_float(py));
+    q = make_float2(__uint_as_float(qx), __uint_as_float(qy));
+}
+__device__ __forceinline__ void xor_swap(double2 &p, double2 &q, const uint32_t mask) {
+    const long long m = (long long)(int)mask;  // sign-extend the all-ones / zero mask
+    long long px = __double_as_longlong(p.x), py = __double_as_longlong(p.y), qx = __double_as_longlong(q.x),
+              qy = __double_as_longlong(q.y);
+    const long long tx = (px ^ qx) & m, ty = (py ^ qy) & m;
+    px ^= tx, qx ^= tx, py ^= ty, qy ^= ty;
+    p = make_double2(__longlong_as_double(px), __longlong_as_double(py));
+    q = make_double2(__longlong_as_double(qx), __longlong_as_double(qy));
+}
+
+template <typename real, int RB, int B, bool ALLJ>
+__device__ __forceinline__ void mat1_swap(typename Cx<real>::amp (&a)[1 << RB], const uint32_t jmask) {
+    uint32_t ones = 0xffffffffu;
+    asm volatile("" : "+r"(ones));  // opaque: a known mask would be folded back into copies
     static_for<0, (1 << RB) / 2>([&](auto G) {
-        constexpr int g = decltype(G)::value;
-        constexpr int j0 = ((g >> B) << (B + 1)) | (g & ((1 << B) - 1));
-        constexpr int j1 = j0 | (1 << B);
-        if ((jmask >> j0) & 1u) {
-            const real tr = re[j0], ti = im[j0];
-            re[j0] = re[j1];
-            im[j0] = im[j1];
-            re[j1] = tr;
-            im[j1] = ti;
-        }
+        constexpr int j0 = pair_j0<B>(decltype(G)::value), j1 = j0 | (1 << B);
+        // branch free: the mask is all ones for a pair that takes part
+        const uint32_t mask = ALLJ ? ones : 0u - ((jmask >> j0) & 1u);
+        xor_swap(a[j0], a[j1], mask);
+    });
+}
+
+// X on register bit B controlled by register bit CB (= 1): a fixed permutation of registers
+template <typename real, int RB, int B, int CB>
+__device__ __forceinline__ void mat1_swap_ctrl(typename Cx<real>::amp (&a)[1 << RB]) {
+    uint32_t ones = 0xffffffffu;
+    asm volatile("" : "+r"(ones));
+    static_for<0, (1 << RB) / 2>([&](auto G) {
+        constexpr int j0 = pair_j0<B>(decltype(G)::value), j1 = j0 | (1 << B);
+        if constexpr ((j0 >> CB) & 1) xor_swap(a[j0], a[j1], ones);
+    });
+}
+
+// ---- butterfly on register bit B: real 2x2 block, then out1 *= c[pair].
+// MODE 0: c = w (thread phase only)            MODE 1: c[g] = v[g] (host factors only)
+// MODE 2: c[g] = w * v[g]                      MODE 3: as 2, v[g] depends on g's low B bits only
+template <typename real, int RB, int B, int MODE>
+__device__ __forceinline__ void bfly(typename Cx<real>::amp (&a)[1 << RB], const real ma, const real mb, const real mc,
+                                     const real md, const typename Cx<real>::amp w, const real *__restrict__ v) {
+    using C = Cx<real>;
+    using amp = typename C::amp;
+    constexpr int NP = (1 << RB) / 2;
+    // distinct factors: one live at a time (registers are the scarce resource here)
+    constexpr int NC = MODE == 2 ? NP : (MODE == 3 ? (1 << B) : 1);
+    static_for<0, NC>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        amp c = w;
+        if constexpr (MODE == 2 || MODE == 3) c = C::cmul(w, v[2 * i], v[2 * i + 1]);
+        static_for<0, NP / NC>([&](auto Hh) {
+            constexpr int g = decltype(Hh)::value * NC + i;
+            constexpr int j0 = pair_j0<B>(g), j1 = j0 | (1 << B);
+            const amp x0 = a[j0], x1 = a[j1];
+            a[j0] = C::rfma(x1, mb, C::rmul(x0, ma));
+            const amp t = C::rfma(x1, md, C::rmul(x0, mc));
+            if constexpr (MODE == 1)
+                a[j1] = C::cmul(t, v[2 * g], v[2 * g + 1]);
+            else
+                a[j1] = C::cmul(t, c.x, c.y);
+        });
     });
 }
 
 // FULL = false leaves out the rarely used op kinds (general per-amplitude DIAG, 4x4 / 8x8 /
-// 16x16 blocks): the common passes then run a kernel a third of the size, which matters
+// 16x16 blocks): the common passes then run a kernel a fraction of the size, which matters
 // because the interpreter's working set of code competes for the instruction cache.
-// PF = true: the next tile is fetched into shared memory by bulk async copies (TMA) while the
-// current one is processed, so that HBM latency overlaps the register work instead of adding
-// to it.  Two tile buffers; the buffer the current tile came from doubles as its exchange
-// scratch.  Needs the phase-0 distribution the planner marks with QB2_FEATURE_PREFETCH.
-template <typename real, int RB, int MAXT, int MINB, bool FULL, bool PF>
+// `l2pf`: while a tile is processed, the lines of the CTA's next tile are requested into L2
+// (cp.async.bulk.prefetch.L2), so that HBM keeps streaming during the register work and the
+// next load phase finds its data on chip.
+template <typename real, int RB, int MAXT, int MINB, bool FULL>
 __global__ void __launch_bounds__(MAXT, MINB)
     pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
-                const real *__restrict__ gcoefs, const uint64_t hi_base, const uint32_t ntiles, const uint32_t roots_off, const uint32_t ctx_off,
-                const uint32_t tile_off, const __grid_constant__ PassParams P) {
+                const uint64_t hi_base, const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off,
+                const uint32_t tile_off, const uint32_t l2pf, const __grid_constant__ PassParams P) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
+    using C = Cx<real>;
+    using amp = typename C::amp;
+    static_assert(sizeof(amp) == sizeof(vec), "an amplitude is one vector register group");
     constexpr int NR = 1 << RB;
     extern __shared__ __align__(16) uint8_t smem[];
 
     const uint32_t tid = threadIdx.x;
-    vec *const roots = reinterpret_cast<vec *>(smem + roots_off);
+    vec *const roots = reinterpret_cast<vec *>(smem);
     if constexpr (std::is_same<real, float>::value) {
         for (uint32_t i = tid; i < NROOT; i += blockDim.x) {
             float s, c;
@@ -311,6 +357,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
     // every descriptor read below is a constant-bank load with a warp-uniform offset
     const uint8_t *const pb = reinterpret_cast<const uint8_t *>(&P);
     const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(pb);
+    const qb2_io *const IO = reinterpret_cast<const qb2_io *>(pb + QB2_IO_OFFSET);  // fixed offsets: immediate operands
     const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(pb + H->phases_off);
     const qb2_op *const ops = reinterpret_cast<const qb2_op *>(pb + H->ops_off);
     const real *const coefs = reinterpret_cast<const real *>(pb + H->coef_off);
@@ -341,7 +388,51 @@ __global__ void __launch_bounds__(MAXT, MINB)
         ctx[p * nthreads + tid] =
             make_uint4((uint32_t)xt, (uint32_t)(xt >> 32), wb * (uint32_t)sizeof(vec), rb * (uint32_t)sizeof(vec));
     }
-    uint8_t *tile_b = smem + tile_off;
+    {  // one more entry: the thread's physical offset at the store (qb2_io.store_col)
+        uint64_t xt = 0;
+        for (int b = 0; b < TB; ++b)
+            if ((tid >> b) & 1u) xt |= IO->store_col[b];
+        ctx[n_phases * nthreads + tid] = make_uint4((uint32_t)xt, (uint32_t)(xt >> 32), 0u, 0u);
+    }
+    // ---- phase slots (qb2_op.b1): a phase made of multiplier ladders is linear in the index bits,
+    // so it is the sum of a thread part (here, once per CTA) and a tile part (once per tile, below)
+    const uint32_t n_slots = H->n_slots;
+    auto two_slots = [&](const qb2_op &op) { return op.kind == QB2_OP_DIAG_BIT && !(op.flags & 1u); };
+    frac *const stile = reinterpret_cast<frac *>(smem + slot_off);                         // [2][QB2_MAX_SLOTS]
+    uint16_t *const slot_op = reinterpret_cast<uint16_t *>(stile + 2 * QB2_MAX_SLOTS);     // [QB2_MAX_SLOTS]
+    frac *const sthr = reinterpret_cast<frac *>(slot_op + QB2_MAX_SLOTS);                  // [n_slots][threads]
+    // value of slot `which` of an op on index x: an op with thread-only ladders AND register-bit
+    // ladders (DIAG_BIT with both phases live) owns two slots: the thread-only sum, then the sum of all
+    auto ladder_sum = [&](const qb2_op &op, const uint32_t which, const uint64_t x) {
+        const qb2_tab *tb = tabs + (op.kind == QB2_OP_BFLY ? (uint32_t)op.tab : (uint32_t)op.data);
+        const int nthr = op.ntab_thr, nall = nthr + op.ntab_reg;
+        const int n = (two_slots(op) && which == 0u) ? nthr : nall;
+        frac r = 0;
+        for (int i = 0; i < n; ++i) r += tab_mul<frac>(tb[i], x);
+        return r;
+    };
+    auto has_slot = [&](const qb2_op &op) {
+        return op.b1 != 0 && (op.kind == QB2_OP_BFLY || op.kind == QB2_OP_DIAG_THR || op.kind == QB2_OP_DIAG_BIT);
+    };
+    if (n_slots) {
+        for (uint32_t p = 0; p < n_phases; ++p) {
+            const uint4 c = ctx[p * nthreads + tid];
+            const uint64_t x = hi_base | ((uint64_t)c.y << 32 | c.x);
+            const uint32_t op_end = phases[p].first_op + phases[p].n_ops;
+            for (uint32_t o = phases[p].first_op; o < op_end; ++o) {
+                const qb2_op &op = ops[o];
+                if (has_slot(op)) {
+                    const uint32_t ns = two_slots(op) ? 2u : 1u;
+                    for (uint32_t w = 0; w < ns; ++w) {
+                        sthr[(op.b1 - 1u + w) * nthreads + tid] = ladder_sum(op, w, x);
+                        if (tid == 0) slot_op[op.b1 - 1u + w] = (uint16_t)(o | (w << 15));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    uint8_t *const tile_b = smem + tile_off;
     const uint8_t *const state_b = reinterpret_cast<const uint8_t *>(state);
 
     auto tile_base = [&](uint32_t t) {
@@ -353,33 +444,31 @@ __global__ void __launch_bounds__(MAXT, MINB)
         return tb;
     };
 
-    // ---- prefetch pipeline state: thread c moves chunk c (16 amplitudes, one 128-byte line)
-    const uint32_t tile_bytes = (uint32_t)sizeof(vec) << H->T;
-    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + tile_off + 2 * tile_bytes);
-    uint64_t ch_goff = 0;  // physical offset of this thread's chunk inside a tile
-    uint32_t ch_soff = 0;  // byte offset of the chunk inside a tile buffer
-    auto prefetch = [&](uint32_t t, uint32_t which) {
-        if (tid == 0) mbar_expect_tx(&mbar[which], tile_bytes);
-        bulk_g2s(smem + tile_off + which * tile_bytes + ch_soff, state_b + (tile_base(t) | ch_goff) * sizeof(vec),
-                 16 * sizeof(vec), &mbar[which]);
-    };
-    if constexpr (PF) {
+    // ---- L2 prefetch: chunk c of a tile is one 128-byte line (16 complex64 / 8 complex128
+    // amplitudes); chunk bit i sits at the physical position the host lists in the pf table
+    constexpr int CHUNK_BITS_LOW = std::is_same<real, float>::value ? 4 : 3;
+    const int chunk_bits = (int)H->T - CHUNK_BITS_LOW;
+    uint64_t ch_goff = 0;
+    const bool do_pf = l2pf == 1u && (H->features & QB2_FEATURE_PREFETCH) != 0;
+    if (do_pf) {
         const uint16_t *pf = a16 + H->pf;
-        for (int i = 0; i < (int)H->T - 4; ++i)
-            if ((tid >> i) & 1u) {
-                ch_goff |= 1ull << (pf[i] & 0xffu);
-                ch_soff |= (uint32_t)sizeof(vec) << (pf[i] >> 8);
-            }
-        if (tid == 0) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-        if (blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+        for (int i = 0; i < chunk_bits; ++i)
+            if ((tid >> i) & 1u) ch_goff |= 1ull << (pf[i] & 0xffu);
     }
+    auto prefetch_tile = [&](uint32_t t) {
+        const uint64_t tb = tile_base(t);
+        const uint16_t *pf = a16 + H->pf;
+        for (uint32_t c = tid; (c >> chunk_bits) == 0; c += nthreads) {
+            uint64_t off = ch_goff;
+            const uint32_t hi = c / nthreads;  // uniform
+            for (int i = TB; i < chunk_bits; ++i)
+                if ((hi >> (i - TB)) & 1u) off |= 1ull << (pf[i] & 0xffu);
+            const uint8_t *g = state_b + (tb | off) * sizeof(vec);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(g) : "memory");
+        }
+    };
 
-    real re[NR], im[NR];
+    amp a[NR];
 
     uint32_t iter = 0;
     for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++iter) {
@@ -387,41 +476,43 @@ __global__ void __launch_bounds__(MAXT, MINB)
         const uint64_t tbase = tile_base(t);
         // ---- phase 0: load
         uint64_t xloc;  // local physical index of this thread's register 0
-        if constexpr (PF) {
-            const uint32_t cur = iter & 1u;
-            const uint4 c = ctx[tid];
-            xloc = tbase | ((uint64_t)c.y << 32 | c.x);
-            tile_b = smem + tile_off + cur * tile_bytes;
-            mbar_wait(&mbar[cur], (iter >> 1) & 1u);
-            // phase-0 layout of the buffer: thread bit b = slot bit b, register j = slot j << TB
-            const uint8_t *rb0 = tile_b + tid * (uint32_t)sizeof(vec);
-            const uint32_t stride = (uint32_t)sizeof(vec) << TB;
-            static_for<0, NR>([&](auto J) {
-                constexpr int j = decltype(J)::value;
-                const vec v = *reinterpret_cast<const vec *>(rb0 + j * stride);
-                re[j] = v.x;
-                im[j] = v.y;
-            });
-            // everyone is done with both buffers (this one: just read; the other: last tile's
-            // exchange scratch): hand the other one to the async proxy for the next tile
-            fence_proxy_async();
-            __syncthreads();
-            if (t + gridDim.x < ntiles) prefetch(t + gridDim.x, cur ^ 1u);
-        } else {
-            const qb2_phase &ph = phases[0];
+        {
             const uint4 c = ctx[tid];
             xloc = tbase | ((uint64_t)c.y << 32 | c.x);
             const uint8_t *gb = state_b + xloc * sizeof(vec);
 #ifndef QB2_NOPIN
             asm volatile("" : "+l"(gb));  // keep base + uniform offset: two adds per address
 #endif
-            const uint64_t *rp = a64 + ph.rphys;
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
-                const vec v = ld_stream(reinterpret_cast<const vec *>(gb + rp[j] * sizeof(vec)));
-                re[j] = v.x;
-                im[j] = v.y;
+                a[j] = __ldcs(reinterpret_cast<const amp *>(gb + IO->load_off[j]));
             });
+        }
+        // ---- tile part of the slotted phases: one thread per slot, while the loads are in flight.
+        // Two buffers: a warp may run one tile ahead of the others, never two (barrier below).
+        const uint32_t spar = (iter & 1u) * QB2_MAX_SLOTS;
+        if (n_slots) {
+            const uint32_t nwarps = nthreads >= 32u ? nthreads >> 5 : 1u;  // tiny registers run less than a warp
+            for (uint32_t sl = tid >> 5; sl < n_slots; sl += nwarps)
+                if ((tid & 31u) == 0u) {
+                    const uint32_t so = slot_op[sl];
+                    stile[spar + sl] = ladder_sum(ops[so & 0x7fffu], so >> 15, tbase);
+                }
+            __syncthreads();
+        }
+        if (l2pf == 2u && t + gridDim.x < ntiles) {
+            // plain L2 prefetch of the CTA's next tile: the same addresses this thread will load, one
+            // request per 128-byte line (the first lane of each 16-lane group)
+            if ((tid & (std::is_same<real, float>::value ? 15u : 7u)) == 0u) {
+                const uint4 c = ctx[tid];
+                const uint8_t *gn = state_b + (tile_base(t + gridDim.x) | ((uint64_t)c.y << 32 | c.x)) * sizeof(vec);
+                static_for<0, NR>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + IO->load_off[j]));
+                });
+            }
+        } else if (do_pf && t + gridDim.x < ntiles) {
+            prefetch_tile(t + gridDim.x);
         }
         for (uint32_t p = 0; p < n_phases; ++p) {
             const qb2_phase &ph = phases[p];
@@ -435,25 +526,17 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         const uint32_t stride = (uint32_t)sizeof(vec) << (xf >> 8 & 0xffu);
                         static_for<0, NR>([&](auto J) {
                             constexpr int j = decltype(J)::value;
-                            vec v;
-                            v.x = re[j];
-                            v.y = im[j];
-                            *reinterpret_cast<vec *>(wp + j * stride) = v;
+                            *reinterpret_cast<amp *>(wp + j * stride) = a[j];
                         });
                     } else {
                         const uint16_t *xw = a16 + ph.xw + TB;
                         static_for<0, NR>([&](auto J) {
                             constexpr int j = decltype(J)::value;
-                            vec v;
-                            v.x = re[j];
-                            v.y = im[j];
-                            *reinterpret_cast<vec *>(tile_b + (c.z ^ (xw[j] * (uint32_t)sizeof(vec)))) = v;
+                            *reinterpret_cast<amp *>(tile_b + (c.z ^ (xw[j] * (uint32_t)sizeof(vec)))) = a[j];
                         });
                     }
                 }
-#ifndef QB2_EXP_NOSYNC
                 __syncthreads();
-#endif
                 {
                     xloc = tbase | ((uint64_t)c.y << 32 | c.x);
                     const uint8_t *rp_ = tile_b + c.w;
@@ -461,97 +544,43 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         const uint32_t stride = (uint32_t)sizeof(vec) << (xf >> 16 & 0xffu);
                         static_for<0, NR>([&](auto J) {
                             constexpr int j = decltype(J)::value;
-                            const vec v = *reinterpret_cast<const vec *>(rp_ + j * stride);
-                            re[j] = v.x;
-                            im[j] = v.y;
+                            a[j] = *reinterpret_cast<const amp *>(rp_ + j * stride);
                         });
                     } else {
                         const uint16_t *xr = a16 + ph.xr + TB;
                         static_for<0, NR>([&](auto J) {
                             constexpr int j = decltype(J)::value;
-                            const vec v =
-                                *reinterpret_cast<const vec *>(tile_b + (c.w ^ (xr[j] * (uint32_t)sizeof(vec))));
-                            re[j] = v.x;
-                            im[j] = v.y;
+                            a[j] = *reinterpret_cast<const amp *>(tile_b + (c.w ^ (xr[j] * (uint32_t)sizeof(vec))));
                         });
                     }
                 }
-#ifndef QB2_EXP_NOSYNC
                 __syncthreads();
-#endif
             }
             const uint64_t X = hi_base | xloc;
             // ---- ops of this phase, on registers
             const uint32_t op_end = ph.first_op + ph.n_ops;
             for (uint32_t o = ph.first_op; o < op_end; ++o) {
                 const qb2_op &op = ops[o];
-                const uint32_t kind = op.kind;
-                if (kind == QB2_OP_BFLY) {
-                    // 2x2 gate on register bit b0, then a phase on its b0=1 output that depends on
-                    // the other register bits (host-computed v[pair]) and on the thread (w1)
-                    const uint32_t fl = op.flags;
-                    vec w1;
-                    w1.x = 1;
-                    w1.y = 0;
-                    if (fl & QB2_BFLY_W) {
-                        const qb2_tab *tb = tabs + op.tab;
-                        const int nreg = op.ntab_reg;
-                        frac s1 = 0;
-                        for (int i = 0; i < nreg; ++i)
-                            s1 += tab_is_mul(tb[i])
-                                      ? tab_mul<frac>(tb[i], X)
-                                      : __ldg(tables + tb[i].off + tab_index(tb[i], X) + tb[i].regoff);
-                        w1 = unit_phase(s1, roots);
-                    }
-                    // REAL 2x2 block only (the planner fuses nothing else); the four entries are
-                    // read once, the pair factors v[] straight from the constant bank
-                    const real *m = coefs + 2 * (size_t)op.data;
-                    const real *v = m + 8;
-                    real ma = m[0], mb = m[2], mc = m[4], md = m[6];
-                    opaque(ma), opaque(mb), opaque(mc), opaque(md);  // no re-reads inside the pair loop
-                    const int b0 = op.b0;
-                    static_for<0, RB>([&](auto B) {
-                        constexpr int bb = decltype(B)::value;
-                        if (b0 == bb) {
-                            static_for<0, NR / 2>([&](auto G) {
-                                constexpr int g = decltype(G)::value;
-                                constexpr int j0 = ((g >> bb) << (bb + 1)) | (g & ((1 << bb) - 1));
-                                constexpr int j1 = j0 | (1 << bb);
-                                const real x0r = re[j0], x0i = im[j0], x1r = re[j1], x1i = im[j1];
-                                re[j0] = fma(ma, x0r, mb * x1r);
-                                im[j0] = fma(ma, x0i, mb * x1i);
-                                const real tr = fma(mc, x0r, md * x1r);
-                                const real ti = fma(mc, x0i, md * x1i);
-                                const real vr = v[2 * g], vi = v[2 * g + 1];
-                                const real cr = fma(w1.x, vr, -w1.y * vi);
-                                const real ci = fma(w1.x, vi, w1.y * vr);
-                                re[j1] = fma(tr, cr, -ti * ci);
-                                im[j1] = fma(tr, ci, ti * cr);
-                            });
-                        }
-                    });
-                } else if (kind >= QB2_OP_DIAG) {
-                    const qb2_tab *tb = tabs + op.data;
-                    frac sum = 0;
-                    const int nthr = op.ntab_thr;
-                    for (int i = 0; i < nthr; ++i)
-                        sum += tab_is_mul(tb[i]) ? tab_mul<frac>(tb[i], X)
-                                                 : __ldg(tables + tb[i].off + tab_index(tb[i], X));
-                    tb += nthr;
-                    const int nreg = op.ntab_reg;
-                    if (kind == QB2_OP_DIAG_THR) {
-                        const vec w = unit_phase(sum, roots);
-                        static_for<0, NR>([&](auto J) {
-                            constexpr int j = decltype(J)::value;
-                            const real xr_ = re[j], xi_ = im[j];
-                            re[j] = fma(xr_, w.x, -xi_ * w.y);
-                            im[j] = fma(xr_, w.y, xi_ * w.x);
-                        });
-                    } else if (kind == QB2_OP_DIAG_BIT) {
-                        // phase depends on the thread and on ONE register bit: two phases per thread
-                        frac s0 = sum, s1 = sum;
+                // ---- thread phases of the op, as turn fractions, in front of the dispatch (the arms below
+                // are register arithmetic): s0 over the descriptors that depend on thread/tile bits only,
+                // s1 = s0 + those that also depend on register bit b0 (their b0=1 half; multiplier
+                // ladders vanish for b0=0).  Slotted ops: two shared-memory reads.
+                frac s0 = 0, s1 = 0;
+                if (op.kind >= QB2_OP_DIAG_THR && op.kind != QB2_OP_DIAG_VEC) {  // DIAG_THR, DIAG_BIT, BFLY
+                    if (op.b1 != 0) {
+                        const uint32_t sl = op.b1 - 1u;
+                        s1 = sthr[sl * nthreads + tid] + stile[spar + sl];
+                        s0 = s1;  // one slot: thread-only ladders (DIAG_THR) or register-bit ladders only
+                        if (two_slots(op)) s1 = sthr[(sl + 1u) * nthreads + tid] + stile[spar + sl + 1u];
+                    } else {
+                        const int nthr = op.ntab_thr, nreg = op.ntab_reg;
+                        const qb2_tab *tb = tabs + (op.kind == QB2_OP_BFLY ? (uint32_t)op.tab : (uint32_t)op.data);
+                        for (int i = 0; i < nthr; ++i)
+                            s0 += tab_is_mul(tb[i]) ? tab_mul<frac>(tb[i], X) : __ldg(tables + tb[i].off + tab_index(tb[i], X));
+                        s1 = s0;
+                        tb += nthr;
                         for (int i = 0; i < nreg; ++i) {
-                            if (tab_is_mul(tb[i])) {  // b0 * (mult * index bits): nothing for b0 = 0
+                            if (tab_is_mul(tb[i])) {
                                 s1 += tab_mul<frac>(tb[i], X);
                             } else {
                                 const frac *e = tables + tb[i].off + tab_index(tb[i], X);
@@ -559,139 +588,195 @@ __global__ void __launch_bounds__(MAXT, MINB)
                                 s1 += __ldg(e + tb[i].regoff);
                             }
                         }
-                        const bool skip0 = (op.flags & 1u) != 0;
-                        vec w0;
-                        w0.x = 1;
-                        w0.y = 0;
-                        if (!skip0) w0 = unit_phase(s0, roots);
-                        const vec w1 = unit_phase(s1, roots);
-                        const int b0 = op.b0;
-                        static_for<0, RB>([&](auto B) {
-                            constexpr int bb = decltype(B)::value;
-                            if (b0 == bb) {
-                                static_for<0, NR>([&](auto J) {
-                                    constexpr int j = decltype(J)::value;
-                                    if constexpr ((j >> bb) & 1) {
-                                        const real xr_ = re[j], xi_ = im[j];
-                                        re[j] = fma(xr_, w1.x, -xi_ * w1.y);
-                                        im[j] = fma(xr_, w1.y, xi_ * w1.x);
-                                    } else {
-                                        if (!skip0) {
-                                            const real xr_ = re[j], xi_ = im[j];
-                                            re[j] = fma(xr_, w0.x, -xi_ * w0.y);
-                                            im[j] = fma(xr_, w0.y, xi_ * w0.x);
-                                        }
-                                    }
-                                });
-                            }
+                    }
+                }
+                // real 2x2 gate on register bit B, then a phase on its B=1 output that depends on the
+                // other register bits (host-computed v[pair]) and on the thread (w1)
+                auto do_bfly = [&](auto B, auto M) {
+                    constexpr int bb = decltype(B)::value, mode = decltype(M)::value;
+                    if constexpr (bb < RB) {
+                        const real *m = coefs + 2 * (size_t)op.data;
+                        amp w1;
+                        w1.x = 1, w1.y = 0;
+                        if constexpr (mode != 1) w1 = unit_phase(s1, roots);
+                        bfly<real, RB, bb, mode>(a, m[0], m[2], m[4], m[6], w1, m + 8);
+                    }
+                };
+                // phase that depends on the thread and on ONE register bit: two phases per thread
+                auto do_diag_bit = [&](auto B, auto S) {
+                    constexpr int bb = decltype(B)::value;
+                    constexpr bool skip0 = decltype(S)::value != 0;
+                    if constexpr (bb < RB) {
+                        const amp w1 = unit_phase(s1, roots);
+                        amp w0 = w1;
+                        if constexpr (!skip0) w0 = unit_phase(s0, roots);
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            if constexpr ((j >> bb) & 1)
+                                a[j] = C::cmul(a[j], w1.x, w1.y);
+                            else if constexpr (!skip0)
+                                a[j] = C::cmul(a[j], w0.x, w0.y);
                         });
-                    } else if (kind == QB2_OP_DIAG_VEC) {
+                    }
+                };
+                // 2x2 gate on register bit B; thread-level controls may diverge, and divergent code
+                // cannot use the uniform datapath: the coefficients are read before the test
+                auto do_mat1 = [&](auto B, auto S, auto A) {
+                    constexpr int bb = decltype(B)::value, shape = decltype(S)::value;
+                    constexpr bool allj = decltype(A)::value != 0;
+                    if constexpr (bb < RB) {
+                        const real *m = coefs + 2 * (size_t)op.data;
+                        real c8[8];
+                        if constexpr (shape != QB2_MAT1_SWAP) {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) c8[k] = m[k];
+                        }
+                        const uint32_t jmask = op.jmask;
+                        if (((X ^ op.cval) & op.cmask) == 0) {
+                            if constexpr (shape == QB2_MAT1_SWAP)
+                                mat1_swap<real, RB, bb, allj>(a, jmask);
+                            else if constexpr (shape == QB2_MAT1_REAL)
+                                mat1_real<real, RB, bb, allj>(a, c8, jmask);
+                            else if constexpr (shape == QB2_MAT1_ANTI)
+                                mat1_anti<real, RB, bb, allj>(a, c8, jmask);
+                            else
+                                mat1_general<real, RB, bb, allj>(a, c8, jmask);
+                        }
+                    }
+                };
+                auto do_swapc = [&](auto B, auto CB) {
+                    constexpr int bb = decltype(B)::value, cb = decltype(CB)::value;
+                    if constexpr (bb < RB && cb < RB && bb != cb) {
+                        if (((X ^ op.cval) & op.cmask) == 0) mat1_swap_ctrl<real, RB, bb, cb>(a);
+                    }
+                };
+                auto do_mat2 = [&](auto B0, auto B1) {
+                    if constexpr (FULL && decltype(B1)::value < RB) {
+                        if (((X ^ op.cval) & op.cmask) == 0)
+                            apply_mat<real, RB, 2, decltype(B0)::value, decltype(B1)::value>(a, coefs + 2 * (size_t)op.data, op.jmask);
+                    }
+                };
+#define IC(v) std::integral_constant<int, v>{}
+#define BFLY_CASES(b)                                           \
+    case QB2_CODE_BFLY + 4 * b + 0: do_bfly(IC(b), IC(0)); break; \
+    case QB2_CODE_BFLY + 4 * b + 1: do_bfly(IC(b), IC(1)); break; \
+    case QB2_CODE_BFLY + 4 * b + 2: do_bfly(IC(b), IC(2)); break; \
+    case QB2_CODE_BFLY + 4 * b + 3: do_bfly(IC(b), IC(3)); break;
+#define DBIT_CASES(b)                                                    \
+    case QB2_CODE_DIAG_BIT + 2 * b + 0: do_diag_bit(IC(b), IC(0)); break; \
+    case QB2_CODE_DIAG_BIT + 2 * b + 1: do_diag_bit(IC(b), IC(1)); break;
+#define MAT1_CASES(b)                                                      \
+    case QB2_CODE_MAT1 + 8 * b + 0: do_mat1(IC(b), IC(0), IC(0)); break;     \
+    case QB2_CODE_MAT1 + 8 * b + 1: do_mat1(IC(b), IC(0), IC(1)); break;     \
+    case QB2_CODE_MAT1 + 8 * b + 2: do_mat1(IC(b), IC(1), IC(0)); break;     \
+    case QB2_CODE_MAT1 + 8 * b + 3: do_mat1(IC(b), IC(1), IC(1)); break;     \
+    case QB2_CODE_MAT1 + 8 * b + 4: do_mat1(IC(b), IC(2), IC(0)); break;     \
+    case QB2_CODE_MAT1 + 8 * b + 5: do_mat1(IC(b), IC(2), IC(1)); break;     \
+    case QB2_CODE_MAT1 + 8 * b + 6: do_mat1(IC(b), IC(3), IC(0)); break;     \
+    case QB2_CODE_MAT1 + 8 * b + 7: do_mat1(IC(b), IC(3), IC(1)); break;
+#define SWAPC_CASES(b)                                                 \
+    case QB2_CODE_SWAPC + 5 * b + 0: do_swapc(IC(b), IC(0)); break;      \
+    case QB2_CODE_SWAPC + 5 * b + 1: do_swapc(IC(b), IC(1)); break;      \
+    case QB2_CODE_SWAPC + 5 * b + 2: do_swapc(IC(b), IC(2)); break;      \
+    case QB2_CODE_SWAPC + 5 * b + 3: do_swapc(IC(b), IC(3)); break;      \
+    case QB2_CODE_SWAPC + 5 * b + 4: do_swapc(IC(b), IC(4)); break;
+                switch (op.code) {
+                    BFLY_CASES(0) BFLY_CASES(1) BFLY_CASES(2) BFLY_CASES(3) BFLY_CASES(4)
+                    DBIT_CASES(0) DBIT_CASES(1) DBIT_CASES(2) DBIT_CASES(3) DBIT_CASES(4)
+                    MAT1_CASES(0) MAT1_CASES(1) MAT1_CASES(2) MAT1_CASES(3) MAT1_CASES(4)
+                    SWAPC_CASES(0) SWAPC_CASES(1) SWAPC_CASES(2) SWAPC_CASES(3) SWAPC_CASES(4)
+                    case QB2_CODE_DIAG_THR: {
+                        const amp w0 = unit_phase(s0, roots);
+                        static_for<0, NR>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
+                            a[j] = C::cmul(a[j], w0.x, w0.y);
+                        });
+                        break;
+                    }
+                    case QB2_CODE_DIAG_VEC: {
                         // phases that depend on register bits only: host-computed, uniform
                         const real *cv = coefs + 2 * (size_t)op.data;
                         static_for<0, NR>([&](auto J) {
                             constexpr int j = decltype(J)::value;
-                            const real wr = cv[2 * j], wi = cv[2 * j + 1];
-                            const real xr_ = re[j], xi_ = im[j];
-                            re[j] = fma(xr_, wr, -xi_ * wi);
-                            im[j] = fma(xr_, wi, xi_ * wr);
+                            a[j] = C::cmul(a[j], cv[2 * j], cv[2 * j + 1]);
                         });
-                    } else if constexpr (FULL) {  // QB2_OP_DIAG: general, one table sum per amplitude
-                        const frac *t0 = tables, *t1 = tables, *t2 = tables, *t3 = tables;
-                        const uint16_t *g0 = a16, *g1 = a16, *g2 = a16, *g3 = a16;
-                        t0 = tables + tb[0].off + tab_index(tb[0], X);
-                        g0 = a16 + tb[0].regoff;
-                        if (nreg > 1) {
-                            t1 = tables + tb[1].off + tab_index(tb[1], X);
-                            g1 = a16 + tb[1].regoff;
-                        }
-                        if (nreg > 2) {
-                            t2 = tables + tb[2].off + tab_index(tb[2], X);
-                            g2 = a16 + tb[2].regoff;
-                        }
-                        if (nreg > 3) {
-                            t3 = tables + tb[3].off + tab_index(tb[3], X);
-                            g3 = a16 + tb[3].regoff;
-                        }
-                        static_for<0, NR>([&](auto J) {
-                            constexpr int j = decltype(J)::value;
-                            frac s = sum + __ldg(t0 + g0[j]);
-                            if (nreg > 1) s += __ldg(t1 + g1[j]);
-                            if (nreg > 2) s += __ldg(t2 + g2[j]);
-                            if (nreg > 3) s += __ldg(t3 + g3[j]);
-                            const vec w = unit_phase(s, roots);
-                            const real xr_ = re[j], xi_ = im[j];
-                            re[j] = fma(xr_, w.x, -xi_ * w.y);
-                            im[j] = fma(xr_, w.y, xi_ * w.x);
-                        });
+                        break;
                     }
-                } else {
-                  // The thread-level control below may diverge, and divergent code cannot use the
-                  // uniform datapath: read the 2x2 coefficients before it.
-                  const real *m = coefs + 2 * (size_t)op.data;
-                  real c8[8];
-                  if (kind == QB2_OP_MAT1) {
-#pragma unroll
-                      for (int k = 0; k < 8; ++k) c8[k] = m[k];
-                  }
-                  if (((X ^ op.cval) & op.cmask) == 0) {
-                    const uint32_t jmask = op.jmask;
-                    const int b0 = op.b0, b1 = op.b1;
-                    if (kind == QB2_OP_MAT1) {
-                        const uint32_t shape = op.flags;
-
-                        if (shape == QB2_MAT1_SWAP) {
-                            static_for<0, RB>([&](auto B) {
-                                if (b0 == decltype(B)::value) mat1_swap<real, RB, decltype(B)::value>(re, im, jmask);
-                            });
-                        } else if (shape == QB2_MAT1_REAL) {
-                            const real a = c8[0], b = c8[2], c = c8[4], d = c8[6];
-                            static_for<0, RB>([&](auto B) {
-                                if (b0 == decltype(B)::value)
-                                    mat1_real<real, RB, decltype(B)::value>(re, im, a, b, c, d, jmask);
-                            });
-                        } else if (shape == QB2_MAT1_ANTI) {
-                            const real pr = c8[2], pi = c8[3], qr = c8[4], qi = c8[5];
-                            static_for<0, RB>([&](auto B) {
-                                if (b0 == decltype(B)::value)
-                                    mat1_anti<real, RB, decltype(B)::value>(re, im, pr, pi, qr, qi, jmask);
-                            });
-                        } else {
-                            static_for<0, RB>([&](auto B) {
-                                if (b0 == decltype(B)::value)
-                                    mat1_general<real, RB, decltype(B)::value>(re, im, c8, jmask);
+                    case QB2_CODE_DIAG_GEN: {
+                        if constexpr (FULL) {  // general: one table sum per amplitude
+                            const int nthr = op.ntab_thr, nreg = op.ntab_reg;
+                            const qb2_tab *tb = tabs + op.data;
+                            frac sum = 0;  // thread tables again as a fraction (w0 above is already a phase)
+                            for (int i = 0; i < nthr; ++i)
+                                sum += tab_is_mul(tb[i]) ? tab_mul<frac>(tb[i], X) : __ldg(tables + tb[i].off + tab_index(tb[i], X));
+                            tb += nthr;
+                            const frac *t0 = tables, *t1 = tables, *t2 = tables, *t3 = tables;
+                            const uint16_t *g0 = a16, *g1 = a16, *g2 = a16, *g3 = a16;
+                            t0 = tables + tb[0].off + tab_index(tb[0], X);
+                            g0 = a16 + tb[0].regoff;
+                            if (nreg > 1) {
+                                t1 = tables + tb[1].off + tab_index(tb[1], X);
+                                g1 = a16 + tb[1].regoff;
+                            }
+                            if (nreg > 2) {
+                                t2 = tables + tb[2].off + tab_index(tb[2], X);
+                                g2 = a16 + tb[2].regoff;
+                            }
+                            if (nreg > 3) {
+                                t3 = tables + tb[3].off + tab_index(tb[3], X);
+                                g3 = a16 + tb[3].regoff;
+                            }
+                            static_for<0, NR>([&](auto J) {
+                                constexpr int j = decltype(J)::value;
+                                frac sj = sum + __ldg(t0 + g0[j]);
+                                if (nreg > 1) sj += __ldg(t1 + g1[j]);
+                                if (nreg > 2) sj += __ldg(t2 + g2[j]);
+                                if (nreg > 3) sj += __ldg(t3 + g3[j]);
+                                const amp w = unit_phase(sj, roots);
+                                a[j] = C::cmul(a[j], w.x, w.y);
                             });
                         }
-                    } else if constexpr (FULL) {
-                        if (kind == QB2_OP_MAT2) {
-                            static_for<0, RB>([&](auto B0) {
-                                static_for<decltype(B0)::value + 1, RB>([&](auto B1) {
-                                    if (b0 == decltype(B0)::value && b1 == decltype(B1)::value)
-                                        apply_mat<real, RB, 2, decltype(B0)::value, decltype(B1)::value>(re, im, m, jmask);
-                                });
-                            });
-                        } else if (kind == QB2_OP_MAT3) {
-                            if constexpr (RB >= 3) apply_mat<real, RB, 3, 0, 1, 2>(re, im, m, jmask);
-                        } else if (kind == QB2_OP_MAT4) {
-                            if constexpr (RB >= 4) apply_mat<real, RB, 4, 0, 1, 2, 3>(re, im, m, jmask);
-                        }
+                        break;
                     }
-                  }
+                    case QB2_CODE_MAT2 + 0: do_mat2(IC(0), IC(1)); break;
+                    case QB2_CODE_MAT2 + 1: do_mat2(IC(0), IC(2)); break;
+                    case QB2_CODE_MAT2 + 2: do_mat2(IC(0), IC(3)); break;
+                    case QB2_CODE_MAT2 + 3: do_mat2(IC(0), IC(4)); break;
+                    case QB2_CODE_MAT2 + 4: do_mat2(IC(1), IC(2)); break;
+                    case QB2_CODE_MAT2 + 5: do_mat2(IC(1), IC(3)); break;
+                    case QB2_CODE_MAT2 + 6: do_mat2(IC(1), IC(4)); break;
+                    case QB2_CODE_MAT2 + 7: do_mat2(IC(2), IC(3)); break;
+                    case QB2_CODE_MAT2 + 8: do_mat2(IC(2), IC(4)); break;
+                    case QB2_CODE_MAT2 + 9: do_mat2(IC(3), IC(4)); break;
+                    case QB2_CODE_MAT3:
+                        if constexpr (FULL && RB >= 3) {
+                            if (((X ^ op.cval) & op.cmask) == 0) apply_mat<real, RB, 3, 0, 1, 2>(a, coefs + 2 * (size_t)op.data, op.jmask);
+                        }
+                        break;
+                    case QB2_CODE_MAT4:
+                        if constexpr (FULL && RB >= 4) {
+                            if (((X ^ op.cval) & op.cmask) == 0) apply_mat<real, RB, 4, 0, 1, 2, 3>(a, coefs + 2 * (size_t)op.data, op.jmask);
+                        }
+                        break;
+                    default: break;
                 }
+#undef IC
+#undef BFLY_CASES
+#undef DBIT_CASES
+#undef MAT1_CASES
+#undef SWAPC_CASES
             }
         }
         // ---- store with the last phase's distribution
         {
-            const uint64_t *rp = a64 + phases[n_phases - 1].rphys;
-            uint8_t *gb = reinterpret_cast<uint8_t *>(state) + xloc * sizeof(vec);
+            const uint4 c = ctx[n_phases * nthreads + tid];
+            uint8_t *gb = reinterpret_cast<uint8_t *>(state) + (tbase | ((uint64_t)c.y << 32 | c.x)) * sizeof(vec);
 #ifndef QB2_NOPIN
             asm volatile("" : "+l"(gb));
 #endif
             static_for<0, NR>([&](auto J) {
                 constexpr int j = decltype(J)::value;
-                vec v;
-                v.x = re[j];
-                v.y = im[j];
-                st_stream(reinterpret_cast<vec *>(gb + rp[j] * sizeof(vec)), v);
+                __stcs(reinterpret_cast<amp *>(gb + IO->store_off[j]), a[j]);
             });
         }
     }
@@ -710,27 +795,24 @@ __global__ void init_basis_kernel(typename Traits<real>::vec *__restrict__ state
     }
 }
 
-struct Variant {
-    const void *fn;
-    int rb, maxt;
-    bool attr_set;
-};
-
-template <typename real, int RB, int MAXT, int MINB, bool FULL, bool PF>
+template <typename real, int RB, int MAXT, int MINB, bool FULL>
 int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
                   cudaStream_t s) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
-    auto kern = pass_kernel<real, RB, MAXT, MINB, FULL, PF>;
+    auto kern = pass_kernel<real, RB, MAXT, MINB, FULL>;
     static bool attr_set = false;
     static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
+    static const uint32_t l2pf = getenv("QB2_L2PF") ? (uint32_t)atoi(getenv("QB2_L2PF")) : 0u;
     const uint32_t threads = 1u << (h->T - RB);
-    const uint32_t roots_off = 0;
     const uint32_t ctx_off = std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0;
-    const uint32_t tile_off = ctx_off + h->n_phases * threads * 16u;
-    // PF: two tile buffers + two mbarriers; else one exchange buffer when there is an exchange
-    const size_t tile_bytes = PF ? 2 * ((size_t)sizeof(vec) << h->T) + 16
-                                 : (h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0);
+    if (h->n_slots > QB2_MAX_SLOTS) return set_error(QB2_ELIMIT, "pass uses %u phase slots (at most %d)", h->n_slots, QB2_MAX_SLOTS);
+    const uint32_t slot_off = ctx_off + (h->n_phases + 1) * threads * 16u;
+    const uint32_t slot_bytes =
+        h->n_slots ? (uint32_t)(2 * QB2_MAX_SLOTS * sizeof(frac) + QB2_MAX_SLOTS * 2 + (size_t)h->n_slots * threads * sizeof(frac)) : 0u;
+    const uint32_t tile_off = (slot_off + slot_bytes + 15u) & ~15u;
+    // one exchange buffer when there is an exchange
+    const size_t tile_bytes = h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0;
     const size_t smem = tile_off + tile_bytes;
     if (!attr_set) {
         QB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -751,9 +833,7 @@ int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const
     static PassParams params;
     memcpy(&params, h, h->small_bytes);
     const frac *tables = reinterpret_cast<const frac *>(reinterpret_cast<const uint8_t *>(blob_dev) + h->tab_off);
-    const real *gcoefs = reinterpret_cast<const real *>(reinterpret_cast<const uint8_t *>(blob_dev) + h->coef_off);
-    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, gcoefs, hi_base, ntiles, roots_off, ctx_off,
-                                     tile_off, params);
+    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, hi_base, ntiles, ctx_off, slot_off, tile_off, l2pf, params);
     count_launch();
     return check_cuda(cudaGetLastError(), "pass_kernel launch");
 }
@@ -761,19 +841,10 @@ int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const
 template <typename real, int RB, int MAXT, int MINB>
 int launch_variant(void *state, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, uint32_t ntiles,
                    cudaStream_t s) {
-    // the host says which op kinds the pass contains and whether its phase-0 distribution
-    // suits the prefetch pipeline (header.features)
-    static const bool no_pf = getenv("QB2_PREFETCH") == nullptr;  // experimental: slower than direct loads on B200
-    if constexpr (std::is_same<real, float>::value && RB == 4 && MAXT == 256) {
-        if ((h->features & QB2_FEATURE_PREFETCH) && h->T == 12 && !no_pf && ntiles >= 2) {
-            if (h->features & QB2_FEATURE_FULL)
-                return launch_kernel<real, RB, MAXT, 2, true, true>(state, hi_base, h, blob_dev, ntiles, s);
-            return launch_kernel<real, RB, MAXT, 3, false, true>(state, hi_base, h, blob_dev, ntiles, s);
-        }
-    }
+    // the host says which op kinds the pass contains (header.features)
     if (h->features & QB2_FEATURE_FULL)
-        return launch_kernel<real, RB, MAXT, MINB, true, false>(state, hi_base, h, blob_dev, ntiles, s);
-    return launch_kernel<real, RB, MAXT, MINB, false, false>(state, hi_base, h, blob_dev, ntiles, s);
+        return launch_kernel<real, RB, MAXT, MINB, true>(state, hi_base, h, blob_dev, ntiles, s);
+    return launch_kernel<real, RB, MAXT, MINB, false>(state, hi_base, h, blob_dev, ntiles, s);
 }
 
 }  // namespace
@@ -795,6 +866,9 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
     if (n - (int)h->T > 31) return set_error(QB2_ELIMIT, "qb2_run_pass: too many tiles");
     const uint32_t ntiles = 1u << (n - h->T);
     const int tb = h->T - h->r;
+#ifdef QB2_ONLY_F5  // development builds: one variant, for SASS inspection
+    if (dtype == QB2_C64 && h->r == 5 && tb <= 8) return launch_kernel<float, 5, 256, 2, false>(state, hi_base, h, blob_dev, ntiles, s);
+#else
     if (dtype == QB2_C64) {
         if (h->r == 4 && tb <= 8) return launch_variant<float, 4, 256, QB2_MINB4>(state, hi_base, h, blob_dev, ntiles, s);
         if (h->r == 4 && tb == 9) return launch_variant<float, 4, 512, 2>(state, hi_base, h, blob_dev, ntiles, s);
@@ -804,6 +878,7 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
         if (h->r == 3 && tb <= 8) return launch_variant<double, 3, 256, 4>(state, hi_base, h, blob_dev, ntiles, s);
         if (h->r == 4 && tb <= 8) return launch_variant<double, 4, 256, 2>(state, hi_base, h, blob_dev, ntiles, s);
     }
+#endif
     return set_error(QB2_ELIMIT, "qb2_run_pass: no kernel variant for dtype=%d r=%u T=%u", dtype, h->r, h->T);
 }
 

@@ -35,14 +35,52 @@ OP_MAT = {1: 1, 2: 2, 3: 3, 4: 4}
 OP_DIAG, OP_DIAG_THR, OP_DIAG_BIT, OP_DIAG_VEC = 5, 6, 7, 8
 MAT1_GENERAL, MAT1_REAL, MAT1_ANTI, MAT1_SWAP = 0, 1, 2, 3
 OP_BFLY = 9
-BFLY_REAL, BFLY_V, BFLY_W = 1, 2, 4
+BFLY_REAL, BFLY_V, BFLY_W, BFLY_VLOW = 1, 2, 4, 8
 MAX_SEGS = 16
 MAX_PHASES = 8
 MAX_SMALL_BYTES = 8192
+MAX_SLOTS = 32
+SMEM_PER_CTA = 113 * 1024  # two CTAs per SM
 MAX_TAB_BITS = 10
 MAX_PIECES = 6
 MAX_REG_TABS = 4
 HEADER_BYTES = 128
+IO_BYTES = 640  # qb2_io: register offsets at the load and at the store, thread columns of the store
+
+
+# dispatch codes of the pass kernel (include/qrisp_b200.h QB2_CODE_*)
+CODE_BFLY, CODE_DIAG_THR, CODE_DIAG_VEC, CODE_DIAG_GEN, CODE_DIAG_BIT = 0, 20, 21, 22, 24
+CODE_MAT1, CODE_SWAPC, CODE_MAT2, CODE_MAT3, CODE_MAT4 = 34, 74, 99, 109, 110
+
+
+def op_code(kind, b0, b1, flags, jmask, NR):
+    """The single number the kernel switches on: op kind x register bit x variant."""
+    if kind == OP_BFLY:
+        mode = 0 if not flags & BFLY_V else (1 if not flags & BFLY_W else (3 if flags & BFLY_VLOW else 2))
+        return CODE_BFLY + 4 * b0 + mode
+    if kind == OP_DIAG_THR:
+        return CODE_DIAG_THR
+    if kind == OP_DIAG_VEC:
+        return CODE_DIAG_VEC
+    if kind == OP_DIAG:
+        return CODE_DIAG_GEN
+    if kind == OP_DIAG_BIT:
+        return CODE_DIAG_BIT + 2 * b0 + (flags & 1)
+    if kind == 1:
+        if flags == MAT1_SWAP and b1:
+            return CODE_SWAPC + 5 * b0 + (b1 - 1)
+        allj = 1 if jmask == (1 << NR) - 1 else 0
+        return CODE_MAT1 + 8 * b0 + 2 * flags + allj
+    if kind == 2:
+        pairs = [(a, b) for a in range(5) for b in range(a + 1, 5)]
+        return CODE_MAT2 + pairs.index((b0, b1))
+    return CODE_MAT3 if kind == 3 else CODE_MAT4
+
+
+def pack_op(cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags, tab, NR):
+    assert data < 65536
+    return struct.pack("<QQIHHBBBBBBH", cmask, cval, jmask, data, op_code(kind, b0, b1, flags, jmask, NR), kind, b0, b1,
+                       nthr, nreg, flags, tab)
 
 
 class PlanConfig:
@@ -69,6 +107,8 @@ class PlanConfig:
         self.conflict_bits = 4 if dtype == QB2_C64 else 3
         self.max_mat = min(self.r, 4)  # widest dense op the pass kernel applies in registers
         self.fuse_bfly = os.environ.get("QB2_NO_BFLY") is None
+        self.store_relabel = os.environ.get("QB2_NO_RELABEL") is None
+        self.phase_slots = os.environ.get("QB2_NO_SLOTS") is None
 
     @property
     def TB(self):
@@ -194,12 +234,14 @@ class Planner:
                 raise RuntimeError(f"planner made no progress on {head[0]}")
             rest = rest2 + tail
             if resolved:
-                steps.extend(self._build_passes(resolved))
+                steps.extend(self._build_passes(resolved)[0])
         return steps, None
 
     def _build_passes(self, rops):
         """One pass for ``rops``; if its descriptor outgrows the shared-memory staging
-        area the list is halved (small states put whole circuits into one tile)."""
+        area the list is halved (small states put whole circuits into one tile).  A pass may
+        relabel tile positions at its store (see :meth:`_build_pass`): ``self.pos`` and the ops
+        still waiting are moved along."""
         lowset = set(range(self.cfg.L))
         need = set()
         for op in rops:
@@ -208,13 +250,21 @@ class Planner:
         need -= lowset
         if len(need) <= self.cfg.T - self.cfg.L:
             try:
-                return [self._build_pass(rops, need)]
+                step, sigma = self._build_pass(rops, need)
+                for q, x in enumerate(self.pos):
+                    self.pos[q] = sigma.get(x, x)
+                return [step], sigma
             except DescriptorOverflow:
                 pass
         if len(rops) == 1:
             raise RuntimeError("a single op does not fit into a pass descriptor")
         half = len(rops) // 2
-        return self._build_passes(rops[:half]) + self._build_passes(rops[half:])
+        first, sig1 = self._build_passes(rops[:half])
+        second, sig2 = self._build_passes([_remap_op(op, sig1) for op in rops[half:]])
+        both = {x: sig2.get(y, y) for x, y in sig1.items()}
+        for x, y in sig2.items():
+            both.setdefault(x, y)
+        return first + second, both
 
     def _resolve(self, op):
         """Replace logical qubits by physical positions (the map may change later)."""
@@ -276,12 +326,13 @@ class Planner:
             assert taken
             if fixed[0] is not None:
                 R = list(fixed[0]) + [x for x in R if x not in fixed[0]]
-            phases.append([R, taken])
+            phases.append([R, taken, fixed[0] is not None])
 
         # fill register sets, keep the low positions on the lanes for the first / last phase
         low_lane = set(tile_pos[: min(cfg.conflict_bits, cfg.TB)])
         for ph in phases:
             R = ph[0]
+            n_targets = len(R)
             for cand in reversed(tile_pos):
                 if len(R) >= cfg.r:
                     break
@@ -292,19 +343,39 @@ class Planner:
                     break
                 if cand not in R:
                     R.append(cand)
+            if not ph[2]:
+                # register bit order: the first gate's target on the HIGHEST bit, fillers lowest.
+                # A butterfly's phases then depend only on register bits below its own
+                # (QB2_BFLY_VLOW): later butterflies and idle registers sit below it.
+                ph[0] = R = R[n_targets:][::-1] + R[:n_targets][::-1]
         default_R = [x for x in reversed(tile_pos) if x not in low_lane][: cfg.r]
         if len(default_R) < cfg.r:
             default_R = list(reversed(tile_pos))[: cfg.r]
         if set(phases[0][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
-            phases.insert(0, [list(default_R), []])
+            phases.insert(0, [list(default_R), [], False])
+        sigma = {}
         if set(phases[-1][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
-            phases.append([list(default_R), []])
+            if cfg.store_relabel:
+                # The last phase holds some of the lowest positions in registers: a store under that
+                # distribution would scatter 8-byte words.  Instead of one more exchange the tile is
+                # stored RELABELLED: the positions on the lane bits trade places with the low
+                # positions, so every 16-lane group still writes one 128-byte line; the qubits
+                # concerned simply live somewhere else from now on (``pos`` follows).
+                tp_last = [x for x in tile_pos if x not in phases[-1][0]]
+                on_lanes = tp_last[: len(low_lane)]
+                movers = [x for x in on_lanes if x not in low_lane]
+                free_low = [x for x in sorted(low_lane) if x not in on_lanes]
+                assert len(movers) == len(free_low)
+                for x, y in zip(movers, free_low):
+                    sigma[x], sigma[y] = y, x
+            else:
+                phases.append([list(default_R), [], False])
         if len(phases) > MAX_PHASES:
             raise DescriptorOverflow(f"{len(phases)} phases in one pass")
-        return self._pack(tile_pos, phases)
+        return self._pack(tile_pos, phases, sigma), sigma
 
     # -------------------------------------------------------------- packing
-    def _pack(self, tile_pos, phases):
+    def _pack(self, tile_pos, phases, sigma=None):
         cfg = self.cfg
         T, r, TB, n = cfg.T, cfg.r, cfg.TB, cfg.n
         NR = 1 << r
@@ -315,6 +386,15 @@ class Planner:
         a16, a64, coefs, tabdescs, tables, ops_b, phases_b = [], [], [], [], [], [], []
         n_tab_entries = 0
         n_gate_ops = 0
+        n_slots = 0
+        # shared memory left for phase slots when two CTAs share an SM (launch_kernel's layout:
+        # root table, per-phase thread contexts, slot area, exchange buffer)
+        fsize = 4 if cfg.dtype == QB2_C64 else 8
+        threads = 1 << TB
+        fixed = (2048 if cfg.dtype == QB2_C64 else 0) + (len(phases) + 1) * threads * 16
+        fixed += (csize << T) if len(phases) > 1 else 0
+        fixed += 2 * MAX_SLOTS * fsize + 2 * MAX_SLOTS + 16
+        slot_cap = max(0, min(MAX_SLOTS, (SMEM_PER_CTA - fixed) // (threads * fsize))) if cfg.phase_slots else 0
 
         def add16(vals):
             off = len(a16)
@@ -328,7 +408,7 @@ class Planner:
 
         prev = None
         op_count = 0
-        for R, pops in phases:
+        for R, pops, _fixed in phases:
             assert len(R) == r and len(set(R)) == r
             TP = [x for x in tile_pos if x not in R]
             pcol = add64(1 << x for x in TP)
@@ -368,6 +448,19 @@ class Planner:
                     tables.append(_to_frac(vals, frac_t))
                     n_tab_entries += len(vals)
 
+            def take_slot(dop):
+                """1 + phase slot for an op whose descriptors are all multiplier ladders, else 0."""
+                nonlocal n_slots
+                need = 2 if dop["kind"] == OP_DIAG_BIT and not dop.get("flags", 0) & 1 else 1
+                if dop["kind"] not in (OP_DIAG_THR, OP_DIAG_BIT) or n_slots + need > slot_cap:
+                    return 0
+                tabs_ = dop["thr"] + dop["reg"]
+                if not tabs_ or any(t[0] != "mul" for t in tabs_):
+                    return 0
+                first = n_slots + 1
+                n_slots += need
+                return first
+
             def emit_diag(dop):
                 nonlocal op_count
                 data = len(tabdescs)
@@ -375,12 +468,8 @@ class Planner:
                     data = len(coefs)
                     coefs.extend(np.exp(2j * np.pi * dop["vec"]))
                 emit_tables(dop)
-                ops_b.append(
-                    struct.pack(
-                        "<QQIIBBBBBBH", 0, 0, 0, data, dop["kind"], dop.get("b0", 0), 0, len(dop["thr"]),
-                        len(dop["reg"]), dop.get("flags", 0), 0,
-                    )
-                )
+                ops_b.append(pack_op(0, 0, 0, data, dop["kind"], dop.get("b0", 0), take_slot(dop), len(dop["thr"]),
+                                     len(dop["reg"]), dop.get("flags", 0), 0, NR))
                 op_count += 1
 
             def diag_run(start):
@@ -432,17 +521,23 @@ class Planner:
                             if vec_op is not None:
                                 flags |= BFLY_V
                                 pairs = [((g >> b0) << (b0 + 1)) | (g & ((1 << b0) - 1)) | (1 << b0) for g in range(NR // 2)]
-                                coefs.extend(np.exp(2j * np.pi * vec_op["vec"][pairs]))
+                                vturns = vec_op["vec"][pairs]
+                                low = np.arange(NR // 2) & ((1 << b0) - 1)
+                                if np.array_equal(vturns, vturns[low]):
+                                    flags |= BFLY_VLOW
+                                coefs.extend(np.exp(2j * np.pi * vturns))
                             else:
                                 coefs.extend(np.ones(NR // 2, dtype=np.complex128))
                             tab0 = len(tabdescs)
                             ntab = 0
+                            slot = 0
                             if bit_op is not None:
                                 flags |= BFLY_W
                                 emit_tables(bit_op)
                                 ntab = len(bit_op["reg"])
+                                slot = take_slot(bit_op)
                             assert tab0 < 65536
-                            ops_b.append(struct.pack("<QQIIBBBBBBH", 0, 0, 0, data, OP_BFLY, b0, 0, 0, ntab, flags, tab0))
+                            ops_b.append(pack_op(0, 0, 0, data, OP_BFLY, b0, slot, 0, ntab, flags, tab0, NR))
                             op_count += 1
                             for d in dops:
                                 if d is not vec_op and d is not bit_op:
@@ -460,27 +555,21 @@ class Planner:
                         jmask |= 1 << j
                 data = len(coefs)
                 coefs.extend(m.reshape(-1))
-                ops_b.append(
-                    struct.pack(
-                        "<QQIIBBBBBBH", cmask, cval, jmask, data, OP_MAT[k], sbits[0], sbits[1] if k > 1 else 0, 0, 0,
-                        _mat1_shape(m) if k == 1 else 0, 0,
-                    )
-                )
+                shape = _mat1_shape(m) if k == 1 else 0
+                b1 = sbits[1] if k > 1 else 0
+                if k == 1 and shape == MAT1_SWAP and len(regc) == 1 and list(regc.values())[0] == 1:
+                    b1 = 1 + list(regc.keys())[0]  # CX inside the registers: a fixed register permutation
+                ops_b.append(pack_op(cmask, cval, jmask, data, OP_MAT[k], sbits[0], b1, 0, 0, shape, 0, NR))
                 op_count += 1
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
-        # ---- prefetch table: where chunk bit i (tile position tile_pos[4+i]) lives in the phase-0
-        # layout of a tile buffer (thread bit b -> slot bit b, register bit i -> slot bit TB+i)
+        # ---- L2 prefetch table: the physical position of every 128-byte line index bit of a tile
+        # (include/qrisp_b200.h qb2_pass_header.pf)
         pf_feature, pf_index = 0, 0
-        R0 = phases[0][0]
-        TP0 = [x for x in tile_pos if x not in R0]
-        if T >= 8 and tile_pos[:4] == [0, 1, 2, 3] and TP0[:4] == [0, 1, 2, 3]:
-            entries = []
-            for x in tile_pos[4:]:
-                slot = TP0.index(x) if x in TP0 else TB + R0.index(x)
-                entries.append(x | (slot << 8))
-            pf_index = add16(entries)
+        low = 4 if cfg.dtype == QB2_C64 else 3  # positions inside one 128-byte line
+        if T > low and tile_pos[:low] == list(range(low)):
+            pf_index = add16(tile_pos[low:])
             pf_feature = 2
 
         # ---- segments: tile id bits -> non-tile local positions
@@ -503,7 +592,7 @@ class Planner:
         def align(x, a):
             return (x + a - 1) // a * a
 
-        off = HEADER_BYTES
+        off = HEADER_BYTES + IO_BYTES
         phases_off = off
         off += 32 * len(phases_b)
         ops_off = off
@@ -525,11 +614,11 @@ class Planner:
         total = align(tab_off + n_tab_entries * np.dtype(frac_t).itemsize, 256)
 
         # ops outside the lean kernel's repertoire (include/qrisp_b200.h QB2_FEATURE_FULL)
-        features = 1 if any(rec[24] in (2, 3, 4, OP_DIAG) for rec in ops_b) else 0
+        features = 1 if any(rec[24] in (2, 3, 4, OP_DIAG) for rec in ops_b) else 0  # rec[24] = qb2_op.kind
         features |= pf_feature
         blob = bytearray(total)
         hdr = struct.pack(
-            "<IIIIBBBBIIIIIIIII2I",
+            "<IIIIBBBBIIIIIIIIIIHH",
             QB2_PASS_MAGIC,
             total,
             small,
@@ -549,11 +638,22 @@ class Planner:
             len(ops_b),
             features,
             pf_index,
+            n_slots,
         )
         assert len(hdr) == 64
         blob[0:64] = hdr
         for i, (s, d, ln) in enumerate(segs):
             blob[64 + 4 * i : 68 + 4 * i] = struct.pack("<BBBB", s, d, ln, 0)
+        # qb2_io: where register j of a thread goes at the load (first phase) and at the store (last)
+        sigma = sigma or {}
+        io = np.zeros(IO_BYTES // 8, dtype=np.uint64)
+        R0, Rl = phases[0][0], phases[-1][0]
+        for j in range(NR):
+            io[j] = sum(((j >> i) & 1) << R0[i] for i in range(r)) * csize
+            io[32 + j] = sum(((j >> i) & 1) << sigma.get(Rl[i], Rl[i]) for i in range(r)) * csize
+        for b, x in enumerate(x for x in tile_pos if x not in Rl):
+            io[64 + b] = 1 << sigma.get(x, x)  # store_col: physical offset of thread bit b at the store
+        blob[HEADER_BYTES : HEADER_BYTES + IO_BYTES] = io.tobytes()
         blob[phases_off : phases_off + 32 * len(phases_b)] = b"".join(phases_b)
         blob[ops_off : ops_off + 32 * len(ops_b)] = b"".join(ops_b)
         if coefs:
@@ -610,6 +710,15 @@ class _RView:
 # ----------------------------------------------------------------------------------------
 # helpers
 # ----------------------------------------------------------------------------------------
+
+
+def _remap_op(op, sigma):
+    """A resolved op after the tile positions moved by ``sigma`` (a store relabel)."""
+    if not sigma:
+        return op
+    if op[0] == "diag":
+        return ("diag", tuple(sigma.get(x, x) for x in op[1]), op[2])
+    return ("mat", tuple(sigma.get(x, x) for x in op[1]), op[2], {sigma.get(x, x): v for x, v in op[3].items()})
 
 
 def _permute_matrix(mat, order):

@@ -66,7 +66,7 @@ def main():
             from qrisp_b200.planner import Planner
 
             pl = Planner(sv.cfg, sv.pos)
-            step = pl._build_pass([("diag", (sv.cfg.n - 1,), np.array([0.0, 0.0]))], set())
+            step, _sigma = pl._build_pass([("diag", (sv.cfg.n - 1,), np.array([0.0, 0.0]))], set())
             from qrisp_b200.engine import Program
 
             prog = Program(sv, [step])
