@@ -15,7 +15,13 @@ $(LIB): $(OBJ)
 	mkdir -p qrisp_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ)
 
+# development build: one kernel variant (complex64, r=5) with time stamps along a tile's life
+# (tools/trace_tile.py)
+trace:
+	mkdir -p qrisp_b200/lib
+	$(NVCC) $(NVCCFLAGS) -DQB2_TRACE -DQB2_ONLY_F5 -shared -o qrisp_b200/lib/libqb2_trace.so $(SRC)
+
 clean:
 	rm -f $(OBJ) $(LIB)
 
-.PHONY: all clean
+.PHONY: all clean trace

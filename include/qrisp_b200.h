@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QB2_ABI_VERSION 5
+#define QB2_ABI_VERSION 6
 
 #define QB2_C64 0
 #define QB2_C128 1
@@ -171,6 +171,10 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_BFLY_REAL 1 /* flags: the 2x2 block is real (always set: the kernel fuses real blocks only) */
 #define QB2_BFLY_V 2    /* flags: v[] present (else 1) */
 #define QB2_BFLY_W 4    /* flags: tables present (else w1 = 1) */
+#define QB2_BFLY_HAD 16 /* flags: the block is s * [[1, 1], [1, -1]]: the kernel computes x0 + x1 and x0 - x1 and
+                           leaves s out; s is the same for every amplitude, so the host folds it into a later
+                           op that multiplies all amplitudes (a 2x2 matrix, a DIAG_VEC) or appends a DIAG_VEC
+                           to the last pass of a plan */
 #define QB2_BFLY_VLOW 8 /* flags: v[pair] depends only on the register bits BELOW b0, i.e. on the low b0
                            bits of the pair number: the kernel forms w1 * v for 2**b0 pairs only */
 
@@ -182,16 +186,16 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 
 /* qb2_op.code: derived from kind / b0 / b1 / flags / jmask by the host so that the kernel decodes an
  * op with ONE jump (register indices must be compile-time constants, hence one arm per bit). */
-#define QB2_CODE_BFLY 0      /* + 4 * b0 + mode; mode 0: w only, 1: v only, 2: w * v[pair], 3: as 2 with VLOW */
-#define QB2_CODE_DIAG_THR 20
-#define QB2_CODE_DIAG_VEC 21
-#define QB2_CODE_DIAG_GEN 22
-#define QB2_CODE_DIAG_BIT 24 /* + 2 * b0 + (flags & 1) */
-#define QB2_CODE_MAT1 34     /* + 8 * b0 + 2 * shape + (jmask == all registers) */
-#define QB2_CODE_SWAPC 74    /* + 5 * b0 + c: X on register bit b0 controlled by register bit c */
-#define QB2_CODE_MAT2 99     /* + index of (b0, b1) in (0,1),(0,2),(0,3),(0,4),(1,2),...,(3,4) */
-#define QB2_CODE_MAT3 109
-#define QB2_CODE_MAT4 110
+#define QB2_CODE_BFLY 0      /* + 8 * b0 + 2 * mode + had; mode 0: w only, 1: v only, 2: w * v[pair], 3: as 2 with VLOW */
+#define QB2_CODE_DIAG_THR 40
+#define QB2_CODE_DIAG_VEC 41
+#define QB2_CODE_DIAG_GEN 42
+#define QB2_CODE_DIAG_BIT 44 /* + 2 * b0 + (flags & 1) */
+#define QB2_CODE_MAT1 54     /* + 8 * b0 + 2 * shape + (jmask == all registers) */
+#define QB2_CODE_SWAPC 94    /* + 5 * b0 + c: X on register bit b0 controlled by register bit c */
+#define QB2_CODE_MAT2 119    /* + index of (b0, b1) in (0,1),(0,2),(0,3),(0,4),(1,2),...,(3,4) */
+#define QB2_CODE_MAT3 129
+#define QB2_CODE_MAT4 130
 /* Fixed block right after the header: byte offset (from the thread's base address) of register j at
  * the load of a tile (first phase's distribution) and at its store, and the physical offset
  * (amplitudes) of thread bit b at the store.  The store may RELABEL tile positions: when the last

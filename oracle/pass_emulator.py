@@ -75,19 +75,19 @@ def _expected_code(op, NR):
     kind, b0, b1, fl = op["kind"], op["b0"], op["b1"], op["flags"]
     if kind == 9:
         mode = 0 if not fl & 2 else (1 if not fl & 4 else (3 if fl & 8 else 2))
-        return 4 * b0 + mode
+        return 8 * b0 + 2 * mode + (1 if fl & 16 else 0)
     if kind in (6, 8, 5):
-        return {6: 20, 8: 21, 5: 22}[kind]
+        return {6: 40, 8: 41, 5: 42}[kind]
     if kind == 7:
-        return 24 + 2 * b0 + (fl & 1)
+        return 44 + 2 * b0 + (fl & 1)
     if kind == 1:
         if fl == 3 and b1:
-            return 74 + 5 * b0 + (b1 - 1)
-        return 34 + 8 * b0 + 2 * fl + (1 if op["jmask"] == (1 << NR) - 1 else 0)
+            return 94 + 5 * b0 + (b1 - 1)
+        return 54 + 8 * b0 + 2 * fl + (1 if op["jmask"] == (1 << NR) - 1 else 0)
     if kind == 2:
         pairs = [(a, c) for a in range(5) for c in range(a + 1, 5)]
-        return 99 + pairs.index((b0, b1))
-    return 109 if kind == 3 else 110
+        return 119 + pairs.index((b0, b1))
+    return 129 if kind == 3 else 130
 
 
 def _tab_index(tab, X):
@@ -207,6 +207,8 @@ def run(blob, state, hi_base=0, report=None):
                     m = (cf[0:8:2] + 1j * cf[1:8:2]).reshape(2, 2)
                     if fl & 1:
                         m = m.real.astype(np.complex128)
+                    if fl & 16:  # QB2_BFLY_HAD: the kernel adds and subtracts, the coefficients are not read
+                        m = np.array([[1, 1], [1, -1]], dtype=np.complex128)
                     v = cf[8::2] + 1j * cf[9::2]
                     s1 = np.zeros(nthreads, dtype=P.frac_t)
                     if fl & 4:

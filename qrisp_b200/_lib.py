@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libqb2.so")
 
-QB2_ABI_VERSION = 5
+QB2_ABI_VERSION = 6
 QB2_C64, QB2_C128 = 0, 1
 QB2_NO_BASIS = (1 << 64) - 1
 

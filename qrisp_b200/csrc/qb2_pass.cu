@@ -201,6 +201,33 @@ __device__ __forceinline__ void st_stream(V *p, const V v) {
     __stcs(p, v);
 }
 
+__device__ __forceinline__ float2 ld_na(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 ld_na(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// ---- development aid (make trace): time stamps of CTA 0 / thread 0 along its first tiles
+#ifdef QB2_TRACE
+#define QB2_TRACE_TILES 24
+#define QB2_TRACE_STAMPS 64
+__device__ unsigned long long qb2_trace_buf[QB2_TRACE_TILES * QB2_TRACE_STAMPS];
+#define TR(k)                                                                                   \
+    do {                                                                                        \
+        if (blockIdx.x == 0 && threadIdx.x == 0 && iter < QB2_TRACE_TILES && (k) < QB2_TRACE_STAMPS) \
+            qb2_trace_buf[iter * QB2_TRACE_STAMPS + (k)] = clock64();                           \
+    } while (0)
+#else
+#define TR(k) \
+    do {      \
+    } while (0)
+#endif
+
 struct PassParams {  // the small section of a pass, passed by value: lives in the constant bank
     uint4 q[QB2_MAX_SMALL_BYTES / 16];
 };
@@ -298,7 +325,8 @@ __device__ __forceinline__ void mat1_swap_ctrl(typename Cx<real>::amp (&a)[1 << 
 // ---- butterfly on register bit B: real 2x2 block, then out1 *= c[pair].
 // MODE 0: c = w (thread phase only)            MODE 1: c[g] = v[g] (host factors only)
 // MODE 2: c[g] = w * v[g]                      MODE 3: as 2, v[g] depends on g's low B bits only
-template <typename real, int RB, int B, int MODE>
+// HAD: the block is the unnormalised Hadamard (add / subtract)
+template <typename real, int RB, int B, int MODE, bool HAD>
 __device__ __forceinline__ void bfly(typename Cx<real>::amp (&a)[1 << RB], const real ma, const real mb, const real mc,
                                      const real md, const typename Cx<real>::amp w, const real *__restrict__ v) {
     using C = Cx<real>;
@@ -314,8 +342,14 @@ __device__ __forceinline__ void bfly(typename Cx<real>::amp (&a)[1 << RB], const
             constexpr int g = decltype(Hh)::value * NC + i;
             constexpr int j0 = pair_j0<B>(g), j1 = j0 | (1 << B);
             const amp x0 = a[j0], x1 = a[j1];
-            a[j0] = C::rfma(x1, mb, C::rmul(x0, ma));
-            const amp t = C::rfma(x1, md, C::rmul(x0, mc));
+            amp t;
+            if constexpr (HAD) {  // s * [[1, 1], [1, -1]] with s left to the host (QB2_BFLY_HAD)
+                a[j0] = C::add(x0, x1);
+                t = C::sub(x0, x1);
+            } else {
+                a[j0] = C::rfma(x1, mb, C::rmul(x0, ma));
+                t = C::rfma(x1, md, C::rmul(x0, mc));
+            }
             if constexpr (MODE == 1)
                 a[j1] = C::cmul(t, v[2 * g], v[2 * g + 1]);
             else
@@ -444,50 +478,35 @@ __global__ void __launch_bounds__(MAXT, MINB)
         return tb;
     };
 
-    // ---- L2 prefetch: chunk c of a tile is one 128-byte line (16 complex64 / 8 complex128
-    // amplitudes); chunk bit i sits at the physical position the host lists in the pf table
-    constexpr int CHUNK_BITS_LOW = std::is_same<real, float>::value ? 4 : 3;
-    const int chunk_bits = (int)H->T - CHUNK_BITS_LOW;
-    uint64_t ch_goff = 0;
-    const bool do_pf = l2pf == 1u && (H->features & QB2_FEATURE_PREFETCH) != 0;
-    if (do_pf) {
-        const uint16_t *pf = a16 + H->pf;
-        for (int i = 0; i < chunk_bits; ++i)
-            if ((tid >> i) & 1u) ch_goff |= 1ull << (pf[i] & 0xffu);
-    }
-    auto prefetch_tile = [&](uint32_t t) {
-        const uint64_t tb = tile_base(t);
-        const uint16_t *pf = a16 + H->pf;
-        for (uint32_t c = tid; (c >> chunk_bits) == 0; c += nthreads) {
-            uint64_t off = ch_goff;
-            const uint32_t hi = c / nthreads;  // uniform
-            for (int i = TB; i < chunk_bits; ++i)
-                if ((hi >> (i - TB)) & 1u) off |= 1ull << (pf[i] & 0xffu);
-            const uint8_t *g = state_b + (tb | off) * sizeof(vec);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;" ::"l"(g) : "memory");
-        }
-    };
-
     amp a[NR];
 
-    uint32_t iter = 0;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++iter) {
-        // ---- physical offset of the tile (tile id bits deposited into the non-tile positions)
-        const uint64_t tbase = tile_base(t);
-        // ---- phase 0: load
-        uint64_t xloc;  // local physical index of this thread's register 0
-        {
-            const uint4 c = ctx[tid];
-            xloc = tbase | ((uint64_t)c.y << 32 | c.x);
-            const uint8_t *gb = state_b + xloc * sizeof(vec);
+    // ---- software pipeline across tiles: the loads of the CTA's next tile are issued in the same
+    // loop that stores the current one (register by register), so they are in flight while the
+    // stores drain and the slots are set up; a tile's life is: ops, [exchange, ops]*, store + load.
+    const uint4 c0 = ctx[tid];
+    const uint64_t xthr0 = (uint64_t)c0.y << 32 | c0.x;  // this thread's offset under the first phase
+    auto load_base = [&](const uint64_t tb) {
+        const uint8_t *gb = state_b + (tb | xthr0) * sizeof(vec);
 #ifndef QB2_NOPIN
-            asm volatile("" : "+l"(gb));  // keep base + uniform offset: two adds per address
+        asm volatile("" : "+l"(gb));  // keep base + uniform offset: two adds per address
 #endif
-            static_for<0, NR>([&](auto J) {
-                constexpr int j = decltype(J)::value;
-                a[j] = __ldcs(reinterpret_cast<const amp *>(gb + IO->load_off[j]));
-            });
-        }
+        return gb;
+    };
+    uint32_t iter = 0;
+    uint32_t t = blockIdx.x;
+    uint64_t tbase = 0;
+    if (t < ntiles) {
+        tbase = tile_base(t);
+        const uint8_t *gb = load_base(tbase);
+        static_for<0, NR>([&](auto J) {
+            constexpr int j = decltype(J)::value;
+            a[j] = ld_na(reinterpret_cast<const amp *>(gb + IO->load_off[j]));
+        });
+    }
+    for (; t < ntiles; t += gridDim.x, ++iter) {
+        TR(0);
+        uint64_t xloc = tbase | xthr0;  // local physical index of this thread's register 0
+        TR(1);
         // ---- tile part of the slotted phases: one thread per slot, while the loads are in flight.
         // Two buffers: a warp may run one tile ahead of the others, never two (barrier below).
         const uint32_t spar = (iter & 1u) * QB2_MAX_SLOTS;
@@ -500,23 +519,11 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 }
             __syncthreads();
         }
-        if (l2pf == 2u && t + gridDim.x < ntiles) {
-            // plain L2 prefetch of the CTA's next tile: the same addresses this thread will load, one
-            // request per 128-byte line (the first lane of each 16-lane group)
-            if ((tid & (std::is_same<real, float>::value ? 15u : 7u)) == 0u) {
-                const uint4 c = ctx[tid];
-                const uint8_t *gn = state_b + (tile_base(t + gridDim.x) | ((uint64_t)c.y << 32 | c.x)) * sizeof(vec);
-                static_for<0, NR>([&](auto J) {
-                    constexpr int j = decltype(J)::value;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + IO->load_off[j]));
-                });
-            }
-        } else if (do_pf && t + gridDim.x < ntiles) {
-            prefetch_tile(t + gridDim.x);
-        }
+        TR(2);
         for (uint32_t p = 0; p < n_phases; ++p) {
             const qb2_phase &ph = phases[p];
             if (p > 0) {
+                TR(4 + 2 * p);
                 // ---- exchange through shared memory
                 const uint4 c = ctx[p * nthreads + tid];
                 const uint32_t xf = ph.xflags;
@@ -555,6 +562,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                     }
                 }
                 __syncthreads();
+                TR(5 + 2 * p);
             }
             const uint64_t X = hi_base | xloc;
             // ---- ops of this phase, on registers
@@ -592,14 +600,15 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 }
                 // real 2x2 gate on register bit B, then a phase on its B=1 output that depends on the
                 // other register bits (host-computed v[pair]) and on the thread (w1)
-                auto do_bfly = [&](auto B, auto M) {
+                auto do_bfly = [&](auto B, auto M, auto Hd) {
                     constexpr int bb = decltype(B)::value, mode = decltype(M)::value;
+                    constexpr bool had = decltype(Hd)::value != 0;
                     if constexpr (bb < RB) {
                         const real *m = coefs + 2 * (size_t)op.data;
                         amp w1;
                         w1.x = 1, w1.y = 0;
                         if constexpr (mode != 1) w1 = unit_phase(s1, roots);
-                        bfly<real, RB, bb, mode>(a, m[0], m[2], m[4], m[6], w1, m + 8);
+                        bfly<real, RB, bb, mode, had>(a, m[0], m[2], m[4], m[6], w1, m + 8);
                     }
                 };
                 // phase that depends on the thread and on ONE register bit: two phases per thread
@@ -657,11 +666,15 @@ __global__ void __launch_bounds__(MAXT, MINB)
                     }
                 };
 #define IC(v) std::integral_constant<int, v>{}
-#define BFLY_CASES(b)                                           \
-    case QB2_CODE_BFLY + 4 * b + 0: do_bfly(IC(b), IC(0)); break; \
-    case QB2_CODE_BFLY + 4 * b + 1: do_bfly(IC(b), IC(1)); break; \
-    case QB2_CODE_BFLY + 4 * b + 2: do_bfly(IC(b), IC(2)); break; \
-    case QB2_CODE_BFLY + 4 * b + 3: do_bfly(IC(b), IC(3)); break;
+#define BFLY_CASES(b)                                                      \
+    case QB2_CODE_BFLY + 8 * b + 0: do_bfly(IC(b), IC(0), IC(0)); break;     \
+    case QB2_CODE_BFLY + 8 * b + 1: do_bfly(IC(b), IC(0), IC(1)); break;     \
+    case QB2_CODE_BFLY + 8 * b + 2: do_bfly(IC(b), IC(1), IC(0)); break;     \
+    case QB2_CODE_BFLY + 8 * b + 3: do_bfly(IC(b), IC(1), IC(1)); break;     \
+    case QB2_CODE_BFLY + 8 * b + 4: do_bfly(IC(b), IC(2), IC(0)); break;     \
+    case QB2_CODE_BFLY + 8 * b + 5: do_bfly(IC(b), IC(2), IC(1)); break;     \
+    case QB2_CODE_BFLY + 8 * b + 6: do_bfly(IC(b), IC(3), IC(0)); break;     \
+    case QB2_CODE_BFLY + 8 * b + 7: do_bfly(IC(b), IC(3), IC(1)); break;
 #define DBIT_CASES(b)                                                    \
     case QB2_CODE_DIAG_BIT + 2 * b + 0: do_diag_bit(IC(b), IC(0)); break; \
     case QB2_CODE_DIAG_BIT + 2 * b + 1: do_diag_bit(IC(b), IC(1)); break;
@@ -760,6 +773,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         break;
                     default: break;
                 }
+                TR(24 + (o < 36u ? o : 36u));
 #undef IC
 #undef BFLY_CASES
 #undef DBIT_CASES
@@ -767,17 +781,30 @@ __global__ void __launch_bounds__(MAXT, MINB)
 #undef SWAPC_CASES
             }
         }
-        // ---- store with the last phase's distribution
+        // ---- store with the last phase's distribution; load the next tile behind every store
         {
+            TR(62);
             const uint4 c = ctx[n_phases * nthreads + tid];
             uint8_t *gb = reinterpret_cast<uint8_t *>(state) + (tbase | ((uint64_t)c.y << 32 | c.x)) * sizeof(vec);
 #ifndef QB2_NOPIN
             asm volatile("" : "+l"(gb));
 #endif
-            static_for<0, NR>([&](auto J) {
-                constexpr int j = decltype(J)::value;
-                __stcs(reinterpret_cast<amp *>(gb + IO->store_off[j]), a[j]);
-            });
+            const uint32_t tn = t + gridDim.x;
+            if (tn < ntiles) {
+                tbase = tile_base(tn);
+                const uint8_t *gn = load_base(tbase);
+                static_for<0, NR>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    __stcs(reinterpret_cast<amp *>(gb + IO->store_off[j]), a[j]);
+                    a[j] = ld_na(reinterpret_cast<const amp *>(gn + IO->load_off[j]));
+                });
+            } else {
+                static_for<0, NR>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    __stcs(reinterpret_cast<amp *>(gb + IO->store_off[j]), a[j]);
+                });
+            }
+            TR(63);
         }
     }
 }
@@ -803,7 +830,7 @@ int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const
     auto kern = pass_kernel<real, RB, MAXT, MINB, FULL>;
     static bool attr_set = false;
     static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
-    static const uint32_t l2pf = getenv("QB2_L2PF") ? (uint32_t)atoi(getenv("QB2_L2PF")) : 0u;
+    static const uint32_t l2pf = getenv("QB2_L2PF") ? (uint32_t)atoi(getenv("QB2_L2PF")) : 4u;
     const uint32_t threads = 1u << (h->T - RB);
     const uint32_t ctx_off = std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0;
     if (h->n_slots > QB2_MAX_SLOTS) return set_error(QB2_ELIMIT, "pass uses %u phase slots (at most %d)", h->n_slots, QB2_MAX_SLOTS);
@@ -813,7 +840,8 @@ int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const
     const uint32_t tile_off = (slot_off + slot_bytes + 15u) & ~15u;
     // one exchange buffer when there is an exchange
     const size_t tile_bytes = h->n_phases > 1 ? ((size_t)sizeof(vec) << h->T) : 0;
-    const size_t smem = tile_off + tile_bytes;
+    static const size_t pad_smem = getenv("QB2_PAD_SMEM") ? (size_t)atoi(getenv("QB2_PAD_SMEM")) : 0;  // experiment
+    const size_t smem = tile_off + tile_bytes + pad_smem;
     if (!attr_set) {
         QB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
@@ -881,6 +909,17 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
 #endif
     return set_error(QB2_ELIMIT, "qb2_run_pass: no kernel variant for dtype=%d r=%u T=%u", dtype, h->r, h->T);
 }
+
+#ifdef QB2_TRACE
+extern "C" int qb2_debug_read_trace(unsigned long long *out, int count) {
+    if (count > QB2_TRACE_TILES * QB2_TRACE_STAMPS) count = QB2_TRACE_TILES * QB2_TRACE_STAMPS;
+    cudaDeviceSynchronize();
+    const cudaError_t e = cudaMemcpyFromSymbol(out, qb2_trace_buf, sizeof(unsigned long long) * count);
+    static unsigned long long zero[QB2_TRACE_TILES * QB2_TRACE_STAMPS];
+    cudaMemcpyToSymbol(qb2_trace_buf, zero, sizeof(zero));
+    return e == cudaSuccess ? count : -1;
+}
+#endif
 
 int launch_init_basis(void *state, int n, uint64_t basis, int dtype, cudaStream_t s) {
     if (!state || n < 0 || n > 40) return set_error(QB2_EINVAL, "qb2_init_basis: bad arguments");

@@ -35,7 +35,7 @@ OP_MAT = {1: 1, 2: 2, 3: 3, 4: 4}
 OP_DIAG, OP_DIAG_THR, OP_DIAG_BIT, OP_DIAG_VEC = 5, 6, 7, 8
 MAT1_GENERAL, MAT1_REAL, MAT1_ANTI, MAT1_SWAP = 0, 1, 2, 3
 OP_BFLY = 9
-BFLY_REAL, BFLY_V, BFLY_W, BFLY_VLOW = 1, 2, 4, 8
+BFLY_REAL, BFLY_V, BFLY_W, BFLY_VLOW, BFLY_HAD = 1, 2, 4, 8, 16
 MAX_SEGS = 16
 MAX_PHASES = 8
 MAX_SMALL_BYTES = 8192
@@ -49,15 +49,15 @@ IO_BYTES = 640  # qb2_io: register offsets at the load and at the store, thread 
 
 
 # dispatch codes of the pass kernel (include/qrisp_b200.h QB2_CODE_*)
-CODE_BFLY, CODE_DIAG_THR, CODE_DIAG_VEC, CODE_DIAG_GEN, CODE_DIAG_BIT = 0, 20, 21, 22, 24
-CODE_MAT1, CODE_SWAPC, CODE_MAT2, CODE_MAT3, CODE_MAT4 = 34, 74, 99, 109, 110
+CODE_BFLY, CODE_DIAG_THR, CODE_DIAG_VEC, CODE_DIAG_GEN, CODE_DIAG_BIT = 0, 40, 41, 42, 44
+CODE_MAT1, CODE_SWAPC, CODE_MAT2, CODE_MAT3, CODE_MAT4 = 54, 94, 119, 129, 130
 
 
 def op_code(kind, b0, b1, flags, jmask, NR):
     """The single number the kernel switches on: op kind x register bit x variant."""
     if kind == OP_BFLY:
         mode = 0 if not flags & BFLY_V else (1 if not flags & BFLY_W else (3 if flags & BFLY_VLOW else 2))
-        return CODE_BFLY + 4 * b0 + mode
+        return CODE_BFLY + 8 * b0 + 2 * mode + (1 if flags & BFLY_HAD else 0)
     if kind == OP_DIAG_THR:
         return CODE_DIAG_THR
     if kind == OP_DIAG_VEC:
@@ -109,6 +109,7 @@ class PlanConfig:
         self.fuse_bfly = os.environ.get("QB2_NO_BFLY") is None
         self.store_relabel = os.environ.get("QB2_NO_RELABEL") is None
         self.phase_slots = os.environ.get("QB2_NO_SLOTS") is None
+        self.had_bfly = os.environ.get("QB2_NO_HAD") is None
 
     @property
     def TB(self):
@@ -175,6 +176,10 @@ class Planner:
         self.pos = pos  # list: logical qubit -> physical position
         self.n_total = cfg.n if n_total is None else n_total
         self.window = window
+        # Hadamard-type butterflies run unnormalised (x0 + x1, x0 - x1): the factor they leave out
+        # is the same for every amplitude, so it is carried here and multiplied in by a later op
+        # that multiplies every amplitude anyway, at the latest by the last pass of plan()
+        self.pending_scale = 1.0
 
     # -------------------------------------------------------------- passes
     def plan(self, ops):
@@ -234,10 +239,14 @@ class Planner:
                 raise RuntimeError(f"planner made no progress on {head[0]}")
             rest = rest2 + tail
             if resolved:
-                steps.extend(self._build_passes(resolved)[0])
+                # the carried scale is settled by the last pass of the plan and in front of anything
+                # that is not a pass (relabels move no data and may follow)
+                nxt = next((op for op in rest if op.kind != "relabel"), None)
+                settle = nxt is None or (nxt.kind == "mat" and len(nxt.targets) > cfg.max_mat)
+                steps.extend(self._build_passes(resolved, settle)[0])
         return steps, None
 
-    def _build_passes(self, rops):
+    def _build_passes(self, rops, settle=True):
         """One pass for ``rops``; if its descriptor outgrows the shared-memory staging
         area the list is halved (small states put whole circuits into one tile).  A pass may
         relabel tile positions at its store (see :meth:`_build_pass`): ``self.pos`` and the ops
@@ -250,7 +259,7 @@ class Planner:
         need -= lowset
         if len(need) <= self.cfg.T - self.cfg.L:
             try:
-                step, sigma = self._build_pass(rops, need)
+                step, sigma = self._build_pass(rops, need, settle)
                 for q, x in enumerate(self.pos):
                     self.pos[q] = sigma.get(x, x)
                 return [step], sigma
@@ -259,8 +268,8 @@ class Planner:
         if len(rops) == 1:
             raise RuntimeError("a single op does not fit into a pass descriptor")
         half = len(rops) // 2
-        first, sig1 = self._build_passes(rops[:half])
-        second, sig2 = self._build_passes([_remap_op(op, sig1) for op in rops[half:]])
+        first, sig1 = self._build_passes(rops[:half], False)
+        second, sig2 = self._build_passes([_remap_op(op, sig1) for op in rops[half:]], settle)
         both = {x: sig2.get(y, y) for x, y in sig1.items()}
         for x, y in sig2.items():
             both.setdefault(x, y)
@@ -283,7 +292,7 @@ class Planner:
         return BigMatStep(tp, op.matrix, cmask, cval)
 
     # -------------------------------------------------------------- one pass
-    def _build_pass(self, rops, tile_need):
+    def _build_pass(self, rops, tile_need, settle=True):
         cfg = self.cfg
         tile = set(range(cfg.L)) | set(tile_need)
         p = 0
@@ -372,10 +381,15 @@ class Planner:
                 phases.append([list(default_R), [], False])
         if len(phases) > MAX_PHASES:
             raise DescriptorOverflow(f"{len(phases)} phases in one pass")
-        return self._pack(tile_pos, phases, sigma), sigma
+        scale0 = self.pending_scale
+        try:
+            return self._pack(tile_pos, phases, sigma, settle), sigma
+        except DescriptorOverflow:
+            self.pending_scale = scale0
+            raise
 
     # -------------------------------------------------------------- packing
-    def _pack(self, tile_pos, phases, sigma=None):
+    def _pack(self, tile_pos, phases, sigma=None, settle=True):
         cfg = self.cfg
         T, r, TB, n = cfg.T, cfg.r, cfg.TB, cfg.n
         NR = 1 << r
@@ -466,7 +480,8 @@ class Planner:
                 data = len(tabdescs)
                 if dop["kind"] == OP_DIAG_VEC:
                     data = len(coefs)
-                    coefs.extend(np.exp(2j * np.pi * dop["vec"]))
+                    coefs.extend(np.exp(2j * np.pi * dop["vec"]) * self.pending_scale)
+                    self.pending_scale = 1.0
                 emit_tables(dop)
                 ops_b.append(pack_op(0, 0, 0, data, dop["kind"], dop.get("b0", 0), take_slot(dop), len(dop["thr"]),
                                      len(dop["reg"]), dop.get("flags", 0), 0, NR))
@@ -516,6 +531,11 @@ class Planner:
                             n_gate_ops += len(terms)
                             i = nxt
                             flags = BFLY_REAL if np.max(np.abs(m.imag)) < 1e-16 else 0
+                            mr = m.real
+                            if cfg.had_bfly and mr[0, 0] != 0 and mr[0, 0] == mr[0, 1] == mr[1, 0] == -mr[1, 1]:
+                                # s * [[1, 1], [1, -1]]: run as add / subtract, s joins the pending scale
+                                flags |= BFLY_HAD
+                                self.pending_scale *= float(mr[0, 0])
                             data = len(coefs)
                             coefs.extend(m.reshape(-1))
                             if vec_op is not None:
@@ -553,14 +573,19 @@ class Planner:
                 for j in range(NR):
                     if all(((j >> b) & 1) == v for b, v in regc.items()):
                         jmask |= 1 << j
+                shape = _mat1_shape(m) if k == 1 else 0
+                if self.pending_scale != 1.0 and not ctrls and not (k == 1 and shape == MAT1_SWAP):
+                    m = m * self.pending_scale  # every amplitude passes through this matrix
+                    self.pending_scale = 1.0
                 data = len(coefs)
                 coefs.extend(m.reshape(-1))
-                shape = _mat1_shape(m) if k == 1 else 0
                 b1 = sbits[1] if k > 1 else 0
                 if k == 1 and shape == MAT1_SWAP and len(regc) == 1 and list(regc.values())[0] == 1:
                     b1 = 1 + list(regc.keys())[0]  # CX inside the registers: a fixed register permutation
                 ops_b.append(pack_op(cmask, cval, jmask, data, OP_MAT[k], sbits[0], b1, 0, 0, shape, 0, NR))
                 op_count += 1
+            if settle and R is phases[-1][0] and self.pending_scale != 1.0:
+                emit_diag({"kind": OP_DIAG_VEC, "vec": np.zeros(NR), "thr": [], "reg": []})
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 

@@ -403,3 +403,50 @@ def test_from_qrisp_reads_the_fields_the_reference_reads():
         bad = _FakeQC(1, 1)
         bad.data.append(_FakeInstr(_FakeOp("c_if_x", C.GATE_X), [bad.qubits[0]], [bad.clbits[0]]))
         Circuit.from_qrisp(bad)
+
+
+def test_unnormalised_butterflies_settle_their_scale():
+    """Hadamard-type butterflies leave their 1/sqrt(2) to the host (QB2_BFLY_HAD): whatever follows
+    -- nothing, only relabels, a matrix too wide for a pass, more passes -- the state the steps
+    leave behind is normalised."""
+    import math
+
+    from qrisp_b200.planner import BFLY_HAD, OP_BFLY
+
+    def bfly_layer(qc, qubits):
+        for q in qubits:
+            qc.h(q)
+            for k in range(q + 1, qc.num_qubits):
+                qc.cp(math.pi / (1 << (k - q)), k, q)
+
+    rng = np.random.default_rng(5)
+    cases = {}
+    qc = Circuit(12)
+    bfly_layer(qc, range(12))
+    cases["qft only"] = qc
+    qc = Circuit(12)
+    bfly_layer(qc, range(6))
+    qc.swap(0, 11)
+    qc.swap(3, 4)
+    cases["relabels last"] = qc
+    qc = Circuit(12)
+    bfly_layer(qc, range(5))
+    a = rng.normal(size=(32, 32)) + 1j * rng.normal(size=(32, 32))
+    qc.unitary(np.linalg.qr(a)[0], (0, 3, 6, 8, 10))  # big path right after unnormalised butterflies
+    bfly_layer(qc, range(5, 9))
+    cases["big matrix in between"] = qc
+    qc = Circuit(12)
+    bfly_layer(qc, range(4))
+    for q in range(12):
+        qc.u3(0.3 + q, 0.2, 0.1, q)  # a general 2x2 absorbs the scale
+    bfly_layer(qc, range(4, 12))
+    cases["absorbed by a matrix"] = qc
+    for name, qc in cases.items():
+        for kw in ({}, {"T": 9, "r": 3}):
+            sv, steps = emulate_statevector(qc, **kw)
+            had = 0
+            for s in steps:
+                if s.kind == "pass":
+                    had += sum(1 for op in pass_emulator.parse(s.blob).ops if op["kind"] == OP_BFLY and op["flags"] & BFLY_HAD)
+            assert had > 0, name
+            np.testing.assert_allclose(sv, ref_sim.statevector(qc), atol=3e-6, err_msg=name)

@@ -35,6 +35,9 @@ def cases(n):
     out["h8"] = circ(lambda qc: [qc.h(q) for q in hi] + [qc.rz(0.3, q) for q in hi] + [qc.h(q) for q in hi])
     out["u3x4"] = circ(lambda qc: [qc.u3(0.3, 0.2, 0.1, q) for q in hi])
     out["u3x16"] = circ(lambda qc: [qc.u3(0.3 + 0.1 * k, 0.2, 0.1, q) or qc.cz(q, (q + 1) % 4) for k in range(4) for q in hi])
+    for reps in (2, 4, 8):  # slope = cost per op once a single-phase pass is compute bound
+        out[f"u3x{4 * reps}_1phase"] = circ(lambda qc, reps=reps: [qc.u3(0.3 + 0.1 * k, 0.2, 0.1, q) or qc.cx(q, (q + 1) % 4) for k in range(reps) for q in hi])
+        out[f"bfly{4 * reps}_1phase"] = circ(lambda qc, reps=reps: [(qc.h(q), [qc.cp(math.pi / (1 << (k - q)), k, q) for k in range(q + 1, n)]) for _ in range(reps) for q in hi])
     out["cx4_thread_ctrl"] = circ(lambda qc: [qc.cx(n - 1, q) for q in hi])
     out["cx4_reg_ctrl"] = circ(lambda qc: [qc.cx(hi[(i + 1) % 4], hi[i]) for i in range(4)])
     out["cp_ladder4"] = circ(lambda qc: [qc.cp(math.pi / (1 << (k - q)), k, q) for q in hi for k in range(q + 1, n)])
