@@ -303,7 +303,7 @@ def run_gpu_arm(args):
     peak, peak_src = measured_peaks()
     achieved = 2 * state_bytes / (pass_avg_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "pass_kernel<float,RB=5,256 threads,2 CTAs/SM,lean>",
+        "kernel": "pass_kernel<float,RB=5,256,2,lean>: packed FP32x2 arithmetic, 2 CTAs x 256 threads per SM, 32 amplitudes per thread",
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,

@@ -196,6 +196,11 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_CODE_MAT2 119    /* + index of (b0, b1) in (0,1),(0,2),(0,3),(0,4),(1,2),...,(3,4) */
 #define QB2_CODE_MAT3 129
 #define QB2_CODE_MAT4 130
+#define QB2_CODE_CHAIN 131   /* + index of (first bit, length) in (1,2),(2,2),(2,3),(3,2),(3,3),(3,4),(4,2),...,(4,5):
+                                this record and the length-1 records after it are butterflies with flags
+                                HAD | V | VLOW on register bits first, first-1, ...; the kernel runs them
+                                as one straight-line sequence (one decode for the whole run) and skips the
+                                member records.  A member's thread phase comes from its slot (b1). */
 /* Fixed block right after the header: byte offset (from the thread's base address) of register j at
  * the load of a tile (first phase's distribution) and at its store, and the physical offset
  * (amplitudes) of thread bit b at the store.  The store may RELABEL tile positions: when the last

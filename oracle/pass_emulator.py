@@ -40,8 +40,22 @@ def parse(blob):
             "<QQIHHBBBBBBH", b, ops_off + 32 * i)
         P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, code=code, kind=kind, b0=b0, b1=b1, nthr=nthr,
                           nreg=nreg, flags=flags, tab=tab))
-        assert code == _expected_code(P.ops[-1], 1 << r), (code, P.ops[-1])
+        assert code == _expected_code(P.ops[-1], 1 << r) or 131 <= code < 141, (code, P.ops[-1])
     P.io = np.frombuffer(b, dtype=np.uint64, count=80, offset=128)
+    # butterfly chains (QB2_CODE_CHAIN): the first record's code names (first bit, length); the
+    # members are consecutive unnormalised butterflies on descending bits inside one phase, each with
+    # v[] that depends on lower bits only, and a slot if it has a thread phase
+    shapes = [(bs, k) for bs in range(1, 5) for k in range(2, bs + 2)]
+    for i, op in enumerate(P.ops):
+        if 131 <= op["code"] < 141:
+            bs, k = shapes[op["code"] - 131]
+            ph = next(p for p in P.phases if p[0] <= i < p[0] + p[1])
+            assert i + k <= ph[0] + ph[1], "chain leaves its phase"
+            for j, m in enumerate(P.ops[i : i + k]):
+                assert m["kind"] == 9 and m["b0"] == bs - j and m["flags"] & 16 and m["flags"] & 2 and m["flags"] & 8, m
+                assert m["b1"] or not m["flags"] & 4, m
+                if j:
+                    assert m["code"] == _expected_code(m, 1 << r)
     # phase slots: every slotted op owns its own slot(s) inside [0, n_slots)
     used = []
     for op in P.ops:

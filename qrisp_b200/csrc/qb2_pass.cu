@@ -659,6 +659,27 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         if (((X ^ op.cval) & op.cmask) == 0) mat1_swap_ctrl<real, RB, bb, cb>(a);
                     }
                 };
+                // run of unnormalised butterflies on register bits BS, BS-1, ... (QB2_CODE_CHAIN): one
+                // decode, straight-line code: the shared-memory reads and the root lookup of one
+                // member overlap the arithmetic of the member before
+                auto do_chain = [&](auto BS, auto N) {
+                    constexpr int bs = decltype(BS)::value, n = decltype(N)::value;
+                    if constexpr (bs < RB) {
+                        static_for<0, n>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            const qb2_op &mo = ops[o + k];
+                            amp w;
+                            w.x = 1, w.y = 0;
+                            if (mo.b1 != 0) {
+                                const uint32_t sl = mo.b1 - 1u;
+                                w = unit_phase((frac)(sthr[sl * nthreads + tid] + stile[spar + sl]), roots);
+                            }
+                            const real *m = coefs + 2 * (size_t)mo.data;
+                            bfly<real, RB, bs - k, 3, true>(a, m[0], m[2], m[4], m[6], w, m + 8);
+                        });
+                        o += n - 1;
+                    }
+                };
                 auto do_mat2 = [&](auto B0, auto B1) {
                     if constexpr (FULL && decltype(B1)::value < RB) {
                         if (((X ^ op.cval) & op.cmask) == 0)
@@ -771,6 +792,16 @@ __global__ void __launch_bounds__(MAXT, MINB)
                             if (((X ^ op.cval) & op.cmask) == 0) apply_mat<real, RB, 4, 0, 1, 2, 3>(a, coefs + 2 * (size_t)op.data, op.jmask);
                         }
                         break;
+                    case QB2_CODE_CHAIN + 0: do_chain(IC(1), IC(2)); break;
+                    case QB2_CODE_CHAIN + 1: do_chain(IC(2), IC(2)); break;
+                    case QB2_CODE_CHAIN + 2: do_chain(IC(2), IC(3)); break;
+                    case QB2_CODE_CHAIN + 3: do_chain(IC(3), IC(2)); break;
+                    case QB2_CODE_CHAIN + 4: do_chain(IC(3), IC(3)); break;
+                    case QB2_CODE_CHAIN + 5: do_chain(IC(3), IC(4)); break;
+                    case QB2_CODE_CHAIN + 6: do_chain(IC(4), IC(2)); break;
+                    case QB2_CODE_CHAIN + 7: do_chain(IC(4), IC(3)); break;
+                    case QB2_CODE_CHAIN + 8: do_chain(IC(4), IC(4)); break;
+                    case QB2_CODE_CHAIN + 9: do_chain(IC(4), IC(5)); break;
                     default: break;
                 }
                 TR(24 + (o < 36u ? o : 36u));

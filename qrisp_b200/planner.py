@@ -51,6 +51,8 @@ IO_BYTES = 640  # qb2_io: register offsets at the load and at the store, thread 
 # dispatch codes of the pass kernel (include/qrisp_b200.h QB2_CODE_*)
 CODE_BFLY, CODE_DIAG_THR, CODE_DIAG_VEC, CODE_DIAG_GEN, CODE_DIAG_BIT = 0, 40, 41, 42, 44
 CODE_MAT1, CODE_SWAPC, CODE_MAT2, CODE_MAT3, CODE_MAT4 = 54, 94, 119, 129, 130
+CODE_CHAIN = 131  # + index of (first bit, length) in CHAIN_SHAPES
+CHAIN_SHAPES = [(bs, n) for bs in range(1, 5) for n in range(2, bs + 2)]
 
 
 def op_code(kind, b0, b1, flags, jmask, NR):
@@ -77,10 +79,41 @@ def op_code(kind, b0, b1, flags, jmask, NR):
     return CODE_MAT3 if kind == 3 else CODE_MAT4
 
 
-def pack_op(cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags, tab, NR):
+def pack_op(cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags, tab, NR, code=None):
     assert data < 65536
-    return struct.pack("<QQIHHBBBBBBH", cmask, cval, jmask, data, op_code(kind, b0, b1, flags, jmask, NR), kind, b0, b1,
-                       nthr, nreg, flags, tab)
+    if code is None:
+        code = op_code(kind, b0, b1, flags, jmask, NR)
+    return struct.pack("<QQIHHBBBBBBH", cmask, cval, jmask, data, code, kind, b0, b1, nthr, nreg, flags, tab)
+
+
+def fuse_butterfly_chains(recs, first, NR):
+    """``recs[first:]`` are the argument tuples of one phase's ops.  Runs of unnormalised butterflies
+    on register bits b, b-1, b-2... become one kernel op (QB2_CODE_CHAIN): the kernel decodes once
+    and runs the members back to back in straight-line code, so the latency of fetching one
+    member's phase hides behind the arithmetic of the one before.  Members keep their own
+    records; a member without v[] gets the (all ones) v[] it carries anyway."""
+    need = BFLY_HAD
+    i = first
+    while i < len(recs):
+        r = recs[i]
+        n = 0
+        if r["kind"] == OP_BFLY:
+            while i + n < len(recs):
+                m = recs[i + n]
+                ok = (m["kind"] == OP_BFLY and m["flags"] & need == need and m["b0"] == r["b0"] - n
+                      and (m["flags"] & BFLY_VLOW or not m["flags"] & BFLY_V)  # v[] must depend on lower bits only
+                      and (m["b1"] != 0 or not m["flags"] & BFLY_W))            # a thread phase needs its slot
+                if not ok:
+                    break
+                n += 1
+        if n >= 2 and (r["b0"], n) in CHAIN_SHAPES:
+            for m in recs[i : i + n]:
+                m["flags"] |= BFLY_V | BFLY_VLOW
+            r["code"] = CODE_CHAIN + CHAIN_SHAPES.index((r["b0"], n))
+            i += n
+        else:
+            i += 1
+
 
 
 class PlanConfig:
@@ -110,6 +143,7 @@ class PlanConfig:
         self.store_relabel = os.environ.get("QB2_NO_RELABEL") is None
         self.phase_slots = os.environ.get("QB2_NO_SLOTS") is None
         self.had_bfly = os.environ.get("QB2_NO_HAD") is None
+        self.fuse_chains = os.environ.get("QB2_NO_CHAIN") is None
 
     @property
     def TB(self):
@@ -397,7 +431,7 @@ class Planner:
         real_t = np.float32 if cfg.dtype == QB2_C64 else np.float64
         frac_t = np.uint32 if cfg.dtype == QB2_C64 else np.uint64
 
-        a16, a64, coefs, tabdescs, tables, ops_b, phases_b = [], [], [], [], [], [], []
+        a16, a64, coefs, tabdescs, tables, recs, phases_b = [], [], [], [], [], [], []
         n_tab_entries = 0
         n_gate_ops = 0
         n_slots = 0
@@ -483,8 +517,8 @@ class Planner:
                     coefs.extend(np.exp(2j * np.pi * dop["vec"]) * self.pending_scale)
                     self.pending_scale = 1.0
                 emit_tables(dop)
-                ops_b.append(pack_op(0, 0, 0, data, dop["kind"], dop.get("b0", 0), take_slot(dop), len(dop["thr"]),
-                                     len(dop["reg"]), dop.get("flags", 0), 0, NR))
+                recs.append(dict(cmask=0, cval=0, jmask=0, data=data, kind=dop["kind"], b0=dop.get("b0", 0), b1=take_slot(dop),
+                                 nthr=len(dop["thr"]), nreg=len(dop["reg"]), flags=dop.get("flags", 0), tab=0))
                 op_count += 1
 
             def diag_run(start):
@@ -557,7 +591,8 @@ class Planner:
                                 ntab = len(bit_op["reg"])
                                 slot = take_slot(bit_op)
                             assert tab0 < 65536
-                            ops_b.append(pack_op(0, 0, 0, data, OP_BFLY, b0, slot, 0, ntab, flags, tab0, NR))
+                            recs.append(dict(cmask=0, cval=0, jmask=0, data=data, kind=OP_BFLY, b0=b0, b1=slot, nthr=0, nreg=ntab,
+                                             flags=flags, tab=tab0))
                             op_count += 1
                             for d in dops:
                                 if d is not vec_op and d is not bit_op:
@@ -582,10 +617,13 @@ class Planner:
                 b1 = sbits[1] if k > 1 else 0
                 if k == 1 and shape == MAT1_SWAP and len(regc) == 1 and list(regc.values())[0] == 1:
                     b1 = 1 + list(regc.keys())[0]  # CX inside the registers: a fixed register permutation
-                ops_b.append(pack_op(cmask, cval, jmask, data, OP_MAT[k], sbits[0], b1, 0, 0, shape, 0, NR))
+                recs.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, kind=OP_MAT[k], b0=sbits[0], b1=b1, nthr=0, nreg=0,
+                                 flags=shape, tab=0))
                 op_count += 1
             if settle and R is phases[-1][0] and self.pending_scale != 1.0:
                 emit_diag({"kind": OP_DIAG_VEC, "vec": np.zeros(NR), "thr": [], "reg": []})
+            if cfg.fuse_chains:
+                fuse_butterfly_chains(recs, first_op, NR)
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
@@ -612,6 +650,8 @@ class Planner:
             i = j + 1
         if len(segs) > MAX_SEGS:
             raise RuntimeError("too many tile segments")
+
+        ops_b = [pack_op(NR=NR, **r) for r in recs]
 
         # ---- layout of the small section
         def align(x, a):
