@@ -208,6 +208,11 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
  * bits, so that the store still writes whole 128-byte lines without another exchange; the host's
  * qubit map follows (this replaces the reference's data-moving TensorFactor.swap, tensor_factor.py:55-65). */
 #define QB2_IO_OFFSET 128
+#define QB2_CODE_DBITS 141   /* this record and the following ones are DIAG_BIT ops with flags & 1 and a slot, one per
+                                register bit set in `tab` of this record, in descending bit order: run as one op */
+#define QB2_CODE_CXL 142     /* + index of (top, length) in (2,2),(3,2),(3,3),(4,2),(4,3),(4,4): this record and the
+                                next length-1 are X on register bit top-k-1 controlled by register bit top-k
+                                (k = 0, 1, ...), no other controls: a CX chain inside the registers, one op */
 typedef struct qb2_io {
     uint64_t load_off[32];
     uint64_t store_off[32];

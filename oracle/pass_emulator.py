@@ -40,7 +40,7 @@ def parse(blob):
             "<QQIHHBBBBBBH", b, ops_off + 32 * i)
         P.ops.append(dict(cmask=cmask, cval=cval, jmask=jmask, data=data, code=code, kind=kind, b0=b0, b1=b1, nthr=nthr,
                           nreg=nreg, flags=flags, tab=tab))
-        assert code == _expected_code(P.ops[-1], 1 << r) or 131 <= code < 141, (code, P.ops[-1])
+        assert code == _expected_code(P.ops[-1], 1 << r) or 131 <= code < 148, (code, P.ops[-1])
     P.io = np.frombuffer(b, dtype=np.uint64, count=80, offset=128)
     # butterfly chains (QB2_CODE_CHAIN): the first record's code names (first bit, length); the
     # members are consecutive unnormalised butterflies on descending bits inside one phase, each with
@@ -56,6 +56,25 @@ def parse(blob):
                 assert m["b1"] or not m["flags"] & 4, m
                 if j:
                     assert m["code"] == _expected_code(m, 1 << r)
+    # fused DIAG_BIT runs (QB2_CODE_DBITS): `tab` of the first record is the mask of the members'
+    # register bits; the members follow in descending bit order, each with flags & 1 and a slot
+    for i, op in enumerate(P.ops):
+        if op["code"] == 141:
+            bits = [bb for bb in range(r - 1, -1, -1) if (op["tab"] >> bb) & 1]
+            ph = next(p for p in P.phases if p[0] <= i < p[0] + p[1])
+            assert len(bits) >= 2 and i + len(bits) <= ph[0] + ph[1]
+            for bb, m in zip(bits, P.ops[i : i + len(bits)]):
+                assert m["kind"] == 7 and m["b0"] == bb and m["flags"] & 1 and m["b1"] and m["nthr"] == 0, m
+    # CX ladders (QB2_CODE_CXL): members are X on bit top-k-1 controlled by register bit top-k, no
+    # controls outside the registers
+    cxl = [(bs, k) for bs in range(2, 5) for k in range(2, bs + 1)]
+    for i, op in enumerate(P.ops):
+        if 142 <= op["code"] < 148:
+            top, k = cxl[op["code"] - 142]
+            ph = next(p for p in P.phases if p[0] <= i < p[0] + p[1])
+            assert i + k <= ph[0] + ph[1]
+            for j, m in enumerate(P.ops[i : i + k]):
+                assert m["kind"] == 1 and m["flags"] == 3 and m["cmask"] == 0 and m["b1"] - 1 == top - j and m["b0"] == top - j - 1, m
     # phase slots: every slotted op owns its own slot(s) inside [0, n_slots)
     used = []
     for op in P.ops:

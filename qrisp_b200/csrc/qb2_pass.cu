@@ -680,6 +680,35 @@ __global__ void __launch_bounds__(MAXT, MINB)
                         o += n - 1;
                     }
                 };
+                // run of DIAG_BIT ops, one per register bit in the mask (QB2_CODE_DBITS): one decode
+                auto do_dbits = [&]() {
+                    const uint32_t mask = op.tab;
+                    uint32_t idx = 0;
+                    static_for<0, RB>([&](auto Bi) {
+                        constexpr int bb = RB - 1 - decltype(Bi)::value;
+                        if ((mask >> bb) & 1u) {
+                            const uint32_t sl = ops[o + idx].b1 - 1u;
+                            ++idx;
+                            const amp w = unit_phase((frac)(sthr[sl * nthreads + tid] + stile[spar + sl]), roots);
+                            static_for<0, NR>([&](auto J) {
+                                constexpr int j = decltype(J)::value;
+                                if constexpr ((j >> bb) & 1) a[j] = C::cmul(a[j], w.x, w.y);
+                            });
+                        }
+                    });
+                    o += idx - 1u;
+                };
+                // CX chain inside the registers (QB2_CODE_CXL): bit TOP controls TOP-1, TOP-1 controls TOP-2...
+                auto do_cxl = [&](auto TOP, auto N) {
+                    constexpr int top = decltype(TOP)::value, n = decltype(N)::value;
+                    if constexpr (top < RB) {
+                        static_for<0, n>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            mat1_swap_ctrl<real, RB, top - k - 1, top - k>(a);
+                        });
+                        o += n - 1;
+                    }
+                };
                 auto do_mat2 = [&](auto B0, auto B1) {
                     if constexpr (FULL && decltype(B1)::value < RB) {
                         if (((X ^ op.cval) & op.cmask) == 0)
@@ -792,6 +821,13 @@ __global__ void __launch_bounds__(MAXT, MINB)
                             if (((X ^ op.cval) & op.cmask) == 0) apply_mat<real, RB, 4, 0, 1, 2, 3>(a, coefs + 2 * (size_t)op.data, op.jmask);
                         }
                         break;
+                    case QB2_CODE_DBITS: do_dbits(); break;
+                    case QB2_CODE_CXL + 0: do_cxl(IC(2), IC(2)); break;
+                    case QB2_CODE_CXL + 1: do_cxl(IC(3), IC(2)); break;
+                    case QB2_CODE_CXL + 2: do_cxl(IC(3), IC(3)); break;
+                    case QB2_CODE_CXL + 3: do_cxl(IC(4), IC(2)); break;
+                    case QB2_CODE_CXL + 4: do_cxl(IC(4), IC(3)); break;
+                    case QB2_CODE_CXL + 5: do_cxl(IC(4), IC(4)); break;
                     case QB2_CODE_CHAIN + 0: do_chain(IC(1), IC(2)); break;
                     case QB2_CODE_CHAIN + 1: do_chain(IC(2), IC(2)); break;
                     case QB2_CODE_CHAIN + 2: do_chain(IC(2), IC(3)); break;

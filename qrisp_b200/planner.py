@@ -86,6 +86,61 @@ def pack_op(cmask, cval, jmask, data, kind, b0, b1, nthr, nreg, flags, tab, NR, 
     return struct.pack("<QQIHHBBBBBBH", cmask, cval, jmask, data, code, kind, b0, b1, nthr, nreg, flags, tab)
 
 
+CODE_DBITS = 141  # run of DIAG_BIT ops, one per register bit (mask of the bits in qb2_op.tab)
+
+
+def fuse_diag_bit_runs(recs, first):
+    """Consecutive DIAG_BIT ops of a phase whose b0=0 phase vanishes, each on its own register bit
+    and with a phase slot, become one kernel op (QB2_CODE_DBITS): one decode, members in descending
+    bit order (diagonal ops commute), straight-line code."""
+    i = first
+    while i < len(recs):
+        n = 0
+        bits = set()
+        while i + n < len(recs):
+            m = recs[i + n]
+            if not (m["kind"] == OP_DIAG_BIT and m["flags"] & 1 and m["b1"] != 0 and m["nthr"] == 0 and m["b0"] not in bits):
+                break
+            bits.add(m["b0"])
+            n += 1
+        if n >= 2:
+            recs[i : i + n] = sorted(recs[i : i + n], key=lambda m: -m["b0"])
+            recs[i]["code"] = CODE_DBITS
+            recs[i]["tab"] = sum(1 << b for b in bits)
+            i += n
+        else:
+            i += max(n, 1)
+
+
+CODE_CXL = 142  # + index of (top control bit, length) in CXL_SHAPES
+CXL_SHAPES = [(bs, n) for bs in range(2, 5) for n in range(2, bs + 1)]
+
+
+def fuse_cx_ladders(recs, first):
+    """X on register bit b-1 controlled by register bit b, then b-2 by b-1, ...: the shape a chain of
+    CX gates takes inside the registers (GHZ preparation, ripple carries).  One kernel op
+    (QB2_CODE_CXL) for the run."""
+    i = first
+    while i < len(recs):
+        r = recs[i]
+        n = 0
+        if r["kind"] == 1 and r["flags"] == MAT1_SWAP and r["b1"]:
+            top = r["b1"] - 1
+            while i + n < len(recs):
+                m = recs[i + n]
+                if not (m["kind"] == 1 and m["flags"] == MAT1_SWAP and m["cmask"] == 0 and m["b1"] - 1 == top - n
+                        and m["b0"] == top - n - 1):
+                    break
+                n += 1
+            while n >= 2 and (top, n) not in CXL_SHAPES:
+                n -= 1
+        if n >= 2:
+            r["code"] = CODE_CXL + CXL_SHAPES.index((top, n))
+            i += n
+        else:
+            i += 1
+
+
 def fuse_butterfly_chains(recs, first, NR):
     """``recs[first:]`` are the argument tuples of one phase's ops.  Runs of unnormalised butterflies
     on register bits b, b-1, b-2... become one kernel op (QB2_CODE_CHAIN): the kernel decodes once
@@ -624,6 +679,8 @@ class Planner:
                 emit_diag({"kind": OP_DIAG_VEC, "vec": np.zeros(NR), "thr": [], "reg": []})
             if cfg.fuse_chains:
                 fuse_butterfly_chains(recs, first_op, NR)
+                fuse_diag_bit_runs(recs, first_op)
+                fuse_cx_ladders(recs, first_op)
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
