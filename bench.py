@@ -57,7 +57,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             self.thread = threading.Thread(target=self._read, daemon=True)
@@ -69,7 +69,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, first=0, last=None):
+        """Summary of the samples [first, last) (the timed region); when the region was too short to
+        catch one, of every sample since the warm-up began (same workload), and the note says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -79,7 +81,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        lines = self.lines[first:last] if last is not None else self.lines[first:]
+        note = "samples inside the timed region"
+        if not lines:
+            lines = self.lines
+            note = "timed region shorter than one sampling period: samples since the start of the warm-up (same workload)"
+        for line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -97,6 +104,7 @@ class ClockSampler:
             "sm_max_mhz": float(max(smax)) if smax else None,
             "power_w_max": float(max(power)) if power else None,
             "samples": len(sm),
+            "note": note,
             "reasons": sorted(reasons),
         }
 
@@ -150,18 +158,21 @@ def run_reference_arm(args):
         return
     n_total = LOCAL_QUBITS + int(np.log2(args.gpus))
     vals = []
+    # the sample register shrinks with the number of steps so that the whole run stays within a few
+    # minutes (about 5-10 s per step at 26 qubits, a factor 2 per qubit)
+    sample_qubits = CPU_SAMPLE_QUBITS if args.steps <= 10 else (CPU_SAMPLE_QUBITS - 1 if args.steps <= 25 else CPU_SAMPLE_QUBITS - 2 if args.steps <= 60 else CPU_SAMPLE_QUBITS - 4)
     for _ in range(min(1, args.warmup)):
-        cpu_gates_per_s(CPU_SAMPLE_QUBITS - 4)
+        cpu_gates_per_s(sample_qubits - 4)
     t_all = time.perf_counter()
     for _ in range(args.steps):
-        g, done, dt = cpu_gates_per_s(CPU_SAMPLE_QUBITS)
+        g, done, dt = cpu_gates_per_s(sample_qubits)
         vals.append(g)
     wall = time.perf_counter() - t_all
-    scale = 2.0 ** (CPU_SAMPLE_QUBITS - n_total)
+    scale = 2.0 ** (sample_qubits - n_total)
     value = float(np.mean(vals)) * scale
     sample = (f"oracle/ref_sim.statevector_reference_path (numpy port of the reference's grouped, sparse-then-dense "
-              f"contraction) on the whole GHZ+QFT circuit at {CPU_SAMPLE_QUBITS} qubits, gates/s scaled by "
-              f"2**({CPU_SAMPLE_QUBITS}-{n_total}) to the {n_total}-qubit workload (dense contractions are linear in "
+              f"contraction) on the whole GHZ+QFT circuit at {sample_qubits} qubits, gates/s scaled by "
+              f"2**({sample_qubits}-{n_total}) to the {n_total}-qubit workload (dense contractions are linear in "
               f"the state size)")
     line = {
         "impl": "reference",
@@ -252,17 +263,20 @@ def run_gpu_arm(args):
         prog.run()
         sv.pos[:] = final_pos
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # the clock sampler streams from before the warm-up (nvidia-smi takes a moment to start); the
+    # samples that fall inside the timed region are picked out by line count below
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     lib.qb2_reset_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     pass_ms = []
     barrier()
     ev_start, ev_end = ev[-2], ev[-1]
+    mark0 = len(sampler.lines)
     ev_start.record()
     marks = []
     for k in range(args.steps):
@@ -275,7 +289,8 @@ def run_gpu_arm(args):
     ev_end.record()
     barrier()
     launches = int(lib.qb2_launch_count())
-    clocks = sampler.stop() if rank == 0 else None
+    mark1 = len(sampler.lines)
+    clocks = sampler.stop(mark0, mark1) if rank == 0 else None
     total_ms = ev_start.elapsed_time(ev_end)
     sweep_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps))
     t = torch.tensor([total_ms, sweep_ms], dtype=torch.float64, device="cuda")
@@ -435,7 +450,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -361,14 +361,16 @@ __device__ __forceinline__ void bfly(typename Cx<real>::amp (&a)[1 << RB], const
 // FULL = false leaves out the rarely used op kinds (general per-amplitude DIAG, 4x4 / 8x8 /
 // 16x16 blocks): the common passes then run a kernel a fraction of the size, which matters
 // because the interpreter's working set of code competes for the instruction cache.
-// `l2pf`: while a tile is processed, the lines of the CTA's next tile are requested into L2
-// (cp.async.bulk.prefetch.L2), so that HBM keeps streaming during the register work and the
-// next load phase finds its data on chip.
+// Experiments that did not pay and are gone from the code: an L2 prefetch of
+// the next tile (bulk or plain prefetch instructions); staggering the start of the CTAs that share
+// an SM; register permutations written as plain copies (the compiler then copies the whole array at
+// every join); folding leading X / CX gates of a phase into the load table / the exchange's read
+// map (the irregular exchange path it forces costs what the gates cost).
 template <typename real, int RB, int MAXT, int MINB, bool FULL>
 __global__ void __launch_bounds__(MAXT, MINB)
     pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
                 const uint64_t hi_base, const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off,
-                const uint32_t tile_off, const uint32_t l2pf, const __grid_constant__ PassParams P) {
+                const uint32_t tile_off, const __grid_constant__ PassParams P) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
     using C = Cx<real>;
@@ -897,7 +899,6 @@ int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const
     auto kern = pass_kernel<real, RB, MAXT, MINB, FULL>;
     static bool attr_set = false;
     static int occ_cache_threads = -1, occ_cache_smem = -1, occ_cache = 0;
-    static const uint32_t l2pf = getenv("QB2_L2PF") ? (uint32_t)atoi(getenv("QB2_L2PF")) : 4u;
     const uint32_t threads = 1u << (h->T - RB);
     const uint32_t ctx_off = std::is_same<real, float>::value ? NROOT * sizeof(float2) : 0;
     if (h->n_slots > QB2_MAX_SLOTS) return set_error(QB2_ELIMIT, "pass uses %u phase slots (at most %d)", h->n_slots, QB2_MAX_SLOTS);
@@ -928,7 +929,7 @@ int launch_kernel(void *state, uint64_t hi_base, const qb2_pass_header *h, const
     static PassParams params;
     memcpy(&params, h, h->small_bytes);
     const frac *tables = reinterpret_cast<const frac *>(reinterpret_cast<const uint8_t *>(blob_dev) + h->tab_off);
-    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, hi_base, ntiles, ctx_off, slot_off, tile_off, l2pf, params);
+    kern<<<grid, threads, smem, s>>>(reinterpret_cast<vec *>(state), tables, hi_base, ntiles, ctx_off, slot_off, tile_off, params);
     count_launch();
     return check_cuda(cudaGetLastError(), "pass_kernel launch");
 }
