@@ -41,7 +41,12 @@ class DeviceOps:
             if o is not None:
                 hv[o : o + len(s.blob)] = np.frombuffer(s.blob, dtype=np.uint8)
         dev = host.to(self.device, non_blocking=True)
-        self._pinned = host  # keep the staging buffer alive until the copy has run
+        # keep the staging buffers alive until the copies have run (bounded: the oldest go first)
+        pinned = getattr(self, "_pinned", None)
+        if not isinstance(pinned, list):
+            pinned = self._pinned = []
+        pinned.append(host)
+        del pinned[:-64]
         self.io["h2d"] += total
         return dev
 
@@ -139,9 +144,34 @@ class StateVector(DeviceOps):
         program.run()
 
     def apply_circuit(self, instructions):
-        prog = self.compile(instructions)
-        prog.run()
-        return prog
+        """Plan and run in one go, STREAMING: every pass is launched the moment the planner has built
+        it (launches are asynchronous), so the host plans pass k+1 while the device sweeps pass k and
+        planning disappears from the wall time except for the first pass.  Returns the step list."""
+        unit_tol = 1e-6 if self.dtype == QB2_C64 else 1e-13
+        ops = normalize_circuit(instructions, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
+        planner = Planner(self.cfg, self.pos)
+        keep = []  # device copies of the blobs stay alive until the launches have been issued
+
+        def launch(step):
+            if step.kind == "pass":
+                small = int.from_bytes(step.blob[8:12], "little")
+                header = ctypes.create_string_buffer(step.blob[:small], small)
+                dev = self._upload_blobs([step], [0], len(step.blob))
+                keep.append((dev, header))
+                self._run_pass(step, header, dev, 0)
+                self.stats["passes"] += 1
+                self.stats["kernel_ops"] += step.n_ops
+                self.stats["gate_ops"] += step.n_gate_ops
+                self.stats["phases"] += step.n_phases
+            else:
+                self._run_big(step)
+                self.stats["gate_ops"] += 1
+
+        steps, need = planner.plan(ops, on_step=launch)
+        if need is not None:
+            raise _lib.Qb2Error(f"op needs non-local positions {need} on a single-device state")
+        self._keep_alive = keep
+        return steps
 
     def apply_matrix(self, matrix, qubits):
         """Drop-in for ``TensorFactor.apply_matrix`` (tensor_factor.py:67-89): ``matrix`` is

@@ -271,11 +271,13 @@ class Planner:
         self.pending_scale = 1.0
 
     # -------------------------------------------------------------- passes
-    def plan(self, ops):
+    def plan(self, ops, on_step=None):
         """Plan ``ops``.  Returns ``(steps, need)``: ``need`` is None when everything was
         planned, else the sorted non-local positions the next op needs as dense targets
         (multi-GPU: the engine swaps them in and calls :meth:`plan` again with
-        ``self.pending``)."""
+        ``self.pending``).  ``on_step(step)`` is called for every step as soon as it is built:
+        the engine launches it right away, so that the device sweeps pass k while the host
+        plans pass k+1."""
         cfg = self.cfg
         pos = self.pos
         lowset = set(range(cfg.L))
@@ -291,6 +293,8 @@ class Planner:
                     self.pending = rest
                     return steps, sorted(p for p in tp if p >= cfg.n)
                 steps.append(self._big_step(first))
+                if on_step is not None:
+                    on_step(steps[-1])
                 rest = rest[1:]
                 continue
             tile_need = set()
@@ -332,7 +336,11 @@ class Planner:
                 # that is not a pass (relabels move no data and may follow)
                 nxt = next((op for op in rest if op.kind != "relabel"), None)
                 settle = nxt is None or (nxt.kind == "mat" and len(nxt.targets) > cfg.max_mat)
-                steps.extend(self._build_passes(resolved, settle)[0])
+                built = self._build_passes(resolved, settle)[0]
+                steps.extend(built)
+                if on_step is not None:
+                    for st in built:
+                        on_step(st)
         return steps, None
 
     def _build_passes(self, rops, settle=True):

@@ -450,3 +450,16 @@ def test_unnormalised_butterflies_settle_their_scale():
                     had += sum(1 for op in pass_emulator.parse(s.blob).ops if op["kind"] == OP_BFLY and op["flags"] & BFLY_HAD)
             assert had > 0, name
             np.testing.assert_allclose(sv, ref_sim.statevector(qc), atol=3e-6, err_msg=name)
+
+
+def test_planner_streams_steps_in_order():
+    """plan(on_step=...) hands every step over as soon as it is built (the engine launches it while
+    the next one is planned): same steps, same order, as the returned list."""
+    from qrisp_b200.planner import PlanConfig, Planner
+
+    qc = ghz_qft_circuit(18)
+    ops = normalize_circuit([i for i in qc.data if i.matrix is not None])
+    seen = []
+    steps, need = Planner(PlanConfig(18, T=11, r=4), [17 - q for q in range(18)]).plan(ops, on_step=seen.append)
+    assert need is None and len(steps) > 1
+    assert [id(s) for s in seen] == [id(s) for s in steps]
