@@ -148,6 +148,9 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
  * pass has the `pf` table: the kernel may fetch tiles with bulk async copies into shared
  * memory, one tile ahead of the one being processed */
 #define QB2_FEATURE_PREFETCH 2u
+#define QB2_FEATURE_ZERO_INPUT 4u /* set by the caller in its copy of the header: the state is |0...0> and has not
+                                     been written yet -- the pass does not read it (amplitude 1 at global index
+                                     0, else 0) and so also does the work of qb2_init_basis */
 
 #define QB2_OP_MAT1 1 /* 2x2 on register bit b0 */
 #define QB2_OP_MAT2 2 /* 4x4 on register bits b0 < b1 (matrix index bit 0 <-> b0) */

@@ -494,16 +494,29 @@ __global__ void __launch_bounds__(MAXT, MINB)
 #endif
         return gb;
     };
+    // QB2_FEATURE_ZERO_INPUT: the state is a fresh |0...0> that nobody has written: nothing is read
+    const bool zero_in = (H->features & QB2_FEATURE_ZERO_INPUT) != 0u;
+    auto synth_tile = [&](const uint64_t tb) {
+        static_for<0, NR>([&](auto J) {
+            a[decltype(J)::value].x = 0;
+            a[decltype(J)::value].y = 0;
+        });
+        if ((hi_base | tb | xthr0) == 0) a[0].x = 1;  // register 0 of this thread is global index 0
+    };
     uint32_t iter = 0;
     uint32_t t = blockIdx.x;
     uint64_t tbase = 0;
     if (t < ntiles) {
         tbase = tile_base(t);
-        const uint8_t *gb = load_base(tbase);
-        static_for<0, NR>([&](auto J) {
-            constexpr int j = decltype(J)::value;
-            a[j] = ld_na(reinterpret_cast<const amp *>(gb + IO->load_off[j]));
-        });
+        if (zero_in) {
+            synth_tile(tbase);
+        } else {
+            const uint8_t *gb = load_base(tbase);
+            static_for<0, NR>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                a[j] = ld_na(reinterpret_cast<const amp *>(gb + IO->load_off[j]));
+            });
+        }
     }
     for (; t < ntiles; t += gridDim.x, ++iter) {
         TR(0);
@@ -859,7 +872,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
             asm volatile("" : "+l"(gb));
 #endif
             const uint32_t tn = t + gridDim.x;
-            if (tn < ntiles) {
+            if (tn < ntiles && !zero_in) {
                 tbase = tile_base(tn);
                 const uint8_t *gn = load_base(tbase);
                 static_for<0, NR>([&](auto J) {
@@ -867,6 +880,13 @@ __global__ void __launch_bounds__(MAXT, MINB)
                     __stcs(reinterpret_cast<amp *>(gb + IO->store_off[j]), a[j]);
                     a[j] = ld_na(reinterpret_cast<const amp *>(gn + IO->load_off[j]));
                 });
+            } else if (tn < ntiles) {
+                static_for<0, NR>([&](auto J) {
+                    constexpr int j = decltype(J)::value;
+                    __stcs(reinterpret_cast<amp *>(gb + IO->store_off[j]), a[j]);
+                });
+                tbase = tile_base(tn);
+                synth_tile(tbase);
             } else {
                 static_for<0, NR>([&](auto J) {
                     constexpr int j = decltype(J)::value;

@@ -17,6 +17,8 @@ from . import _lib
 from .normalize import normalize_circuit
 from .planner import QB2_C64, QB2_C128, PlanConfig, Planner
 
+QB2_FEATURE_ZERO_INPUT = 4  # include/qrisp_b200.h
+
 MIN_QUBITS = 9  # smaller registers are padded with idle |0> qubits (a 4 KB state)
 
 
@@ -51,6 +53,13 @@ class DeviceOps:
         return dev
 
     def _run_pass(self, step, header, dev, offset):
+        if getattr(self, "_fresh", False):
+            # the state is |0...0> and not written yet: the pass synthesises its input
+            # (QB2_FEATURE_ZERO_INPUT, header.features at byte 56) instead of reading 2**n zeros
+            raw = bytearray(header.raw)
+            raw[56:60] = (int.from_bytes(raw[56:60], "little") | QB2_FEATURE_ZERO_INPUT).to_bytes(4, "little")
+            header = ctypes.create_string_buffer(bytes(raw), len(raw))
+            self._fresh = False
         _lib.check(
             self.lib.qb2_run_pass(
                 self.state.data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream()
@@ -58,7 +67,14 @@ class DeviceOps:
             "qb2_run_pass",
         )
 
+    def _materialize(self):
+        """Write |0...0> for real if it is still pending (see :meth:`StateVector.reset`)."""
+        if getattr(self, "_fresh", False):
+            self._fresh = False
+            self._init_basis()
+
     def _run_big(self, s):
+        self._materialize()
         torch = _torch()
         k = len(s.positions)
         m = np.ascontiguousarray(s.matrix, dtype=self.np_dtype)
@@ -119,6 +135,12 @@ class StateVector(DeviceOps):
         return self._scratch
 
     def reset(self):
+        """Back to |0...0>.  Lazy: the first pass that runs synthesises the zeros instead of reading
+        them (one write and one read of the state saved); anything else that looks at the state
+        first makes :meth:`_materialize` write them."""
+        self._fresh = True
+
+    def _init_basis(self):
         _lib.check(self.lib.qb2_init_basis(self.state.data_ptr(), self.n, 0, self.dtype, self._stream()), "qb2_init_basis")
 
     def synchronize(self):
@@ -184,6 +206,7 @@ class StateVector(DeviceOps):
     def statevector(self):
         """The amplitudes in the reference's canonical order (qubit 0 = most significant
         bit; simulator.py:288 / tensor_factor.py:163-169), as a host numpy array."""
+        self._materialize()
         torch = _torch()
         nq = self.num_qubits
         perm = (ctypes.c_int * self.n)()
@@ -202,6 +225,7 @@ class StateVector(DeviceOps):
         return host.view(self.np_dtype).copy()
 
     def norm2(self):
+        self._materialize()
         torch = _torch()
         out = torch.empty(1, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.qb2_norm2(self.state.data_ptr(), self.n, out.data_ptr(), self.dtype, self._stream()), "qb2_norm2")
@@ -210,6 +234,7 @@ class StateVector(DeviceOps):
     def probabilities(self, qubits, to_host=True):
         """Marginal distribution of ``qubits``; ``qubits[0]`` is the most significant bit of
         the outcome index (reference: tensor_factor.py:171-182)."""
+        self._materialize()
         torch = _torch()
         m = len(qubits)
         if m > 30:
@@ -230,6 +255,7 @@ class StateVector(DeviceOps):
     def sample(self, shots, qubits=None, rng=None, uniforms=None):
         """Draw ``shots`` basis states from |amp|^2 and return the outcome integers of
         ``qubits`` (``qubits[0]`` most significant).  Host RNG, so a seed fixes the result."""
+        self._materialize()
         torch = _torch()
         if uniforms is None:
             rng = np.random.default_rng() if rng is None else rng
