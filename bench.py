@@ -229,10 +229,9 @@ def run_gpu_arm(args):
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries exactly one JSON line: NCCL's version banner (printed to stdout when the
-        # image sets NCCL_DEBUG=VERSION) is kept out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL's own log (its version banner goes to stdout
+        # when the image sets NCCL_DEBUG) is sent to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
