@@ -229,9 +229,12 @@ def run_gpu_arm(args):
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries exactly one JSON line: NCCL's own log (its version banner goes to stdout
-        # when the image sets NCCL_DEBUG) is sent to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner
+        # when the image sets NCCL_DEBUG) goes to stderr; the line is written to the saved descriptor
+        sys.stdout.flush()
+        _real_stdout = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = _real_stdout
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
@@ -321,8 +324,8 @@ def run_gpu_arm(args):
     pass_avg_ms = (sweep_ms / args.steps - (comm_ms or 0.0)) / max(1, n_pass)
     peak, peak_src = measured_peaks()
     # algorithmic bytes: every pass reads and writes the local state once, except the first pass of a
-    # step, which synthesises |0...0> instead of reading it (QB2_FEATURE_ZERO_INPUT; single GPU only)
-    first_reads = 0 if world == 1 else 1
+    # step, which synthesises |0...0> instead of reading it (QB2_FEATURE_ZERO_INPUT)
+    first_reads = 0
     bytes_per_launch = (2 * n_pass - 1 + first_reads) * state_bytes / max(1, n_pass)
     achieved = bytes_per_launch / (pass_avg_ms * 1e-3) / 1e9
     # one more, untimed replay with events around every pass: where the step's time goes

@@ -20,6 +20,7 @@ The reference has no counterpart (its simulator is single-process numpy); this i
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -107,10 +108,20 @@ class ShardedStateVector(DeviceOps):
         return self._scratch
 
     def reset(self):
+        """Back to |0...0>.  Lazy, like :meth:`StateVector.reset`: the first pass synthesises the
+        zeros (the one sits on rank 0); anything else that looks at the shard first writes them."""
+        self._fresh_layout = True  # |0...0> is invariant under any relabelling of the qubits (see compile_ops)
+        if getattr(self, "lazy_reset", True):
+            self._fresh = True
+        else:
+            self._init_basis()
+
+    def _init_basis(self):
         basis = 0 if self.rank == 0 else _lib.QB2_NO_BASIS
         _lib.check(self.lib.qb2_init_basis(self.state.data_ptr(), self.n, basis, self.dtype, self._stream()), "qb2_init_basis")
 
     def _permute_local(self, perm):
+        self._materialize()
         arr = (ctypes.c_int * self.n)(*perm)
         _lib.check(
             self.lib.qb2_permute_bits(self.state.data_ptr(), self._scratch.data_ptr(), self.n, arr, self.dtype, self._stream()),
@@ -120,6 +131,7 @@ class ShardedStateVector(DeviceOps):
 
     def _all_to_all(self):
         """state (2**g contiguous chunks) -> scratch: chunk c goes to rank c."""
+        self._materialize()
         self.dist.all_to_all_single(self._scratch, self.state, group=self.group)
         self.state, self._scratch = self._scratch, self.state
 
@@ -136,6 +148,9 @@ class ShardedStateVector(DeviceOps):
 
     def compile_ops(self, ops):
         """Plan with swaps.  ``self.pos`` is advanced to the map after the program."""
+        if getattr(self, "_fresh_layout", False) and self.g > 0 and os.environ.get("QB2_NO_INITIAL_LAYOUT") is None:
+            self._choose_initial_layout(ops)
+        self._fresh_layout = False
         planner = Planner(self.cfg, self.pos, n_total=self.n_total)
         steps = []
         pending = list(ops)
@@ -152,6 +167,25 @@ class ShardedStateVector(DeviceOps):
                 raise RuntimeError("swap planning does not terminate")
             steps.append(self._plan_swap(pending, protect))
         return ShardedProgram(self, steps)
+
+    def _choose_initial_layout(self, ops):
+        """The state is still |0...0>, which does not care which qubit sits where: the qubits that are
+        needed LAST as dense targets (or never) start on the rank bits, so that the first qubit swap
+        happens as late as possible -- for GHZ + QFT one swap instead of two.  Pure bookkeeping:
+        ``pos`` entries trade places, no data moves."""
+        n = self.n
+        first_use = {}
+        for i, op in enumerate(ops):
+            for q in op.nd:
+                first_use.setdefault(q, i)
+        nq = len(self.pos)
+        order = sorted(range(nq), key=lambda q: (first_use.get(q, len(ops) + 1), q))
+        want_global = set(order[nq - self.g :])
+        now_global = {q for q in range(nq) if self.pos[q] >= n}
+        come_in = sorted(now_global - want_global)
+        go_out = sorted(want_global - now_global)
+        for a, b in zip(come_in, go_out):
+            self.pos[a], self.pos[b] = self.pos[b], self.pos[a]
 
     def _plan_swap(self, pending, protect):
         n, g = self.n, self.g
@@ -188,6 +222,7 @@ class ShardedStateVector(DeviceOps):
 
     # ------------------------------------------------------------------ read-out
     def probabilities(self, qubits):
+        self._materialize()
         import torch
 
         m = len(qubits)
@@ -204,6 +239,7 @@ class ShardedStateVector(DeviceOps):
         return probs.cpu().numpy()
 
     def norm2(self):
+        self._materialize()
         import torch
 
         out = torch.empty(1, dtype=torch.float64, device=self.device)
@@ -215,6 +251,7 @@ class ShardedStateVector(DeviceOps):
         """Every rank draws its share of the shots from its shard; rank weights come from an
         all-gather of the shard norms.  All ranks must pass identically seeded ``rng``s.
         Returns the outcome integers on every rank (gathered)."""
+        self._materialize()
         import torch
 
         rng = np.random.default_rng(0) if rng is None else rng
@@ -258,6 +295,7 @@ class ShardedStateVector(DeviceOps):
 
     def statevector(self):
         """Gather the whole state in canonical order on every rank (small registers only)."""
+        self._materialize()
         import torch
 
         if self.n_total > 30:

@@ -44,6 +44,7 @@ def _worker(rank, world, port, case, out_dir):
                 self._scratch = torch.zeros_like(self.state)
 
             def reset(self):
+                self._fresh_layout = True  # as the real reset: the planner may choose who starts on the rank bits
                 self.state.zero_()
                 if self.rank == 0:
                     self.state[0] = 1.0
@@ -131,3 +132,38 @@ def test_eviction_choice_prefers_idle_positions():
     ev = choose_evictions(pending, pos, 8, 2, protect={0, 1, 2, 3})
     # positions 7 (qubit 2) and 6 (qubit 3) are needed soon, 0..3 are protected: evict 4 and 5
     assert ev == [4, 5]
+
+
+def test_initial_layout_halves_the_swaps_of_ghz_qft():
+    """A fresh |0...0> does not care which qubit sits on the rank bits: the sharded engine starts
+    with the qubits that are needed last up there (planning only, no process group needed)."""
+    from qrisp_b200 import distributed as D
+    from qrisp_b200.circuit import ghz_qft_circuit
+    from qrisp_b200.normalize import normalize_circuit
+    from qrisp_b200.planner import PlanConfig, Planner
+
+    def swaps(nq, g, choose):
+        class Shard:
+            pass
+
+        sv = Shard()
+        sv.g, sv.n, sv.n_total = g, nq - g, nq
+        sv.cfg = PlanConfig(sv.n, T=9, r=3)
+        sv.pos = [nq - 1 - q for q in range(nq)]
+        ops = normalize_circuit([i for i in ghz_qft_circuit(nq).data if i.matrix is not None])
+        if choose:
+            D.ShardedStateVector._choose_initial_layout(sv, ops)
+            assert sorted(sv.pos) == list(range(nq))
+        planner = Planner(sv.cfg, sv.pos, n_total=nq)
+        pending, count = list(ops), 0
+        while pending:
+            _, need = planner.plan(pending)
+            if need is None:
+                break
+            pending = planner.pending
+            D.ShardedStateVector._plan_swap(sv, pending, set(range(sv.cfg.L)))
+            count += 1
+        return count
+
+    assert swaps(20, 2, False) == 2
+    assert swaps(20, 2, True) == 1
