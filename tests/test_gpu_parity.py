@@ -306,8 +306,10 @@ def test_backend_object_and_apply_matrix(sim):
     np.testing.assert_allclose(sv.statevector(), want, atol=ATOL64)
 
 
-def test_experimental_prefetch_path_matches(sim, monkeypatch):
-    """The TMA prefetch variant of the pass kernel (off by default) computes the same state."""
+@pytest.mark.parametrize("switch", ["QB2_NO_SLOTS", "QB2_NO_CHAIN", "QB2_NO_HAD", "QB2_NO_RELABEL", "QB2_NO_BFLY"])
+def test_planner_switches_do_not_change_the_state(sim, switch):
+    """Every planner optimisation (phase slots, fused runs, unnormalised butterflies, relabelled
+    stores, butterflies at all) can be switched off; the kernel's plain paths give the same state."""
     import subprocess
     import sys
 
@@ -315,8 +317,36 @@ def test_experimental_prefetch_path_matches(sim, monkeypatch):
         "import sys, numpy as np; sys.path.insert(0, %r); "
         "from qrisp_b200.circuit import ghz_qft_circuit; from qrisp_b200.simulator import statevector_sim; "
         "from oracle import ref_sim; qc = ghz_qft_circuit(20); "
-        "e = np.abs(statevector_sim(qc, T=12, r=4) - ref_sim.statevector(qc)).max(); print('ERR', e); assert e < 1e-5"
+        "e = np.abs(statevector_sim(qc) - ref_sim.statevector(qc)).max(); print('ERR', e); assert e < 1e-5"
     ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, QB2_PREFETCH="1")
+    env = dict(os.environ, **{switch: "1"})
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-1000:] + res.stderr[-2000:]
+
+
+def test_fresh_state_is_zero_state_whoever_looks_first():
+    """reset() is lazy (the first pass synthesises |0...0>); every other way of looking at the state
+    has to find it written."""
+    from qrisp_b200.engine import StateVector
+
+    for n in (3, 11, 16):
+        want = np.zeros(1 << n, dtype=np.complex64)
+        want[0] = 1
+        sv = StateVector(n)
+        np.testing.assert_array_equal(sv.statevector(), want)
+        sv = StateVector(n)
+        assert abs(sv.norm2() - 1.0) < 1e-12
+        sv = StateVector(n)
+        p = sv.probabilities(list(range(min(n, 10))))
+        assert p[0] == 1.0 and p[1:].sum() == 0.0
+        sv = StateVector(n)
+        assert set(sv.sample(64, rng=np.random.default_rng(0)).tolist()) == {0}
+        # after gates, reset brings |0...0> back, through the first pass of the next circuit ...
+        sv.apply_circuit([i for i in ghz_circuit(n).data if i.matrix is not None])
+        sv.reset()  # |0...0> does not care where the qubits sit: the map may stay as it is
+        sv.apply_circuit([i for i in ghz_circuit(n).data if i.matrix is not None])
+        st = sv.statevector()
+        assert abs(abs(st[0]) ** 2 - 0.5) < 1e-6 and abs(abs(st[-1]) ** 2 - 0.5) < 1e-6
+        # ... or is written for real when the next thing is a read-out
+        sv.reset()
+        np.testing.assert_array_equal(sv.statevector(), want)
