@@ -147,7 +147,7 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 /* phase 0 keeps tile positions 0..3 on thread bits 0..3 (one 128-byte line per 16 lanes) and the
  * pass has the `pf` table: the kernel may fetch tiles with bulk async copies into shared
  * memory, one tile ahead of the one being processed */
-#define QB2_FEATURE_PREFETCH 2u
+#define QB2_FEATURE_PREFETCH 2u /* reserved */
 #define QB2_FEATURE_ZERO_INPUT 4u /* set by the caller in its copy of the header: the state is |0...0> and has not
                                      been written yet -- the pass does not read it (amplitude 1 at global index
                                      0, else 0) and so also does the work of qb2_init_basis */
@@ -244,8 +244,7 @@ typedef struct qb2_pass_header { /* 128 bytes */
     uint32_t tab_off;    /* phase tables, after the small section: uint32 (C64) / uint64 (C128) */
     uint32_t n_ops;
     uint32_t features; /* QB2_FEATURE_*: which kernel variant the pass needs */
-    uint16_t pf;       /* QB2_FEATURE_PREFETCH: index into the u16 area of uint16[T-4] (complex128: T-3): the
-                          physical position of every 128-byte-line index bit of a tile */
+    uint16_t pf;       /* reserved (0) */
     uint16_t n_slots;  /* phase slots used by the pass (see qb2_op.b1), at most QB2_MAX_SLOTS */
     qb2_seg seg[QB2_MAX_SEGS];
 } qb2_pass_header;

@@ -189,17 +189,7 @@ __device__ __forceinline__ frac tab_mul(const qb2_tab &t, const uint64_t x) {
     return (frac)m.mult * (frac)v;
 }
 
-__device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
-__device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
 
-template <typename V>
-__device__ __forceinline__ V ld_stream(const V *p) {
-    return __ldcs(p);
-}
-template <typename V>
-__device__ __forceinline__ void st_stream(V *p, const V v) {
-    __stcs(p, v);
-}
 
 __device__ __forceinline__ float2 ld_na(const float2 *p) {
     float2 v;

@@ -692,13 +692,7 @@ class Planner:
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
-        # ---- L2 prefetch table: the physical position of every 128-byte line index bit of a tile
-        # (include/qrisp_b200.h qb2_pass_header.pf)
-        pf_feature, pf_index = 0, 0
-        low = 4 if cfg.dtype == QB2_C64 else 3  # positions inside one 128-byte line
-        if T > low and tile_pos[:low] == list(range(low)):
-            pf_index = add16(tile_pos[low:])
-            pf_feature = 2
+        pf_feature, pf_index = 0, 0  # header.pf / QB2_FEATURE_PREFETCH: reserved (an L2 prefetch of the next tile did not pay)
 
         # ---- segments: tile id bits -> non-tile local positions
         segs = []
