@@ -369,6 +369,6 @@ def sample_counts_sharded(qc, shots, seed=0, group=None, dtype=np.complex64, **e
     measurements.sort(key=lambda x: -x[1])
     mes_qubits = [q for q, _ in measurements]
     outs = sv.sample(int(shots), mes_qubits, rng=np.random.default_rng(seed))
-    vals, counts = np.unique(outs, return_counts=True)
-    width = len(mes_qubits)
-    return {bin(int(v))[2:].zfill(width): int(c) for v, c in zip(vals, counts)}, sv
+    from .simulator import counts_dict
+
+    return counts_dict(outs, len(mes_qubits)), sv

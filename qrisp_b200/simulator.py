@@ -118,6 +118,20 @@ def run(qc, shots=None, token="", dtype=np.complex64, seed=None, return_engine=F
     return res
 
 
+def counts_dict(outcomes, width):
+    """{bitstring: count} of an array of outcome integers, most significant bit first (the
+    reference's label convention, simulator.py:151-203).  The labels are built with numpy (bits ->
+    ASCII bytes -> fixed-width strings): a Python loop over thousands of outcomes costs more than
+    the device needs for a 30-qubit sweep pass."""
+    vals, counts = np.unique(np.asarray(outcomes, dtype=np.uint64), return_counts=True)
+    if width == 0:
+        return {"": int(counts.sum())} if len(vals) else {}
+    shifts = np.arange(width - 1, -1, -1, dtype=np.uint64)
+    chars = (((vals[:, None] >> shifts[None, :]) & np.uint64(1)) + np.uint64(48)).astype(np.uint8)
+    labels = np.ascontiguousarray(chars).view(f"S{width}").ravel()
+    return dict(zip(labels.astype(f"U{width}").tolist(), counts.tolist()))
+
+
 def sample_counts(qc, shots, seed=None, dtype=np.complex64, **engine_kwargs):
     """Counts sampled ON THE DEVICE from the amplitudes (no dense distribution on the host):
     the path for wide registers (``get_measurement`` of 30+ qubits)."""
@@ -128,10 +142,8 @@ def sample_counts(qc, shots, seed=None, dtype=np.complex64, **engine_kwargs):
     measurements.sort(key=lambda x: -x[1])
     mes_qubits = [q for q, _ in measurements]
     outs = sv.sample(int(shots), mes_qubits, rng=np.random.default_rng(seed))
-    vals, counts = np.unique(outs, return_counts=True)
-    width = len(mes_qubits)
     _record_io(sv)
-    return {bin(int(v))[2:].zfill(width): int(c) for v, c in zip(vals, counts)}
+    return counts_dict(outs, len(mes_qubits))
 
 
 def statevector_sim(qc, dtype=np.complex64, **engine_kwargs):
