@@ -1082,9 +1082,18 @@ def _fit_multipliers(terms, regpos, frac_bits):
                 f = int(np.rint((t[1, 1] - np.floor(t[1, 1])) * 4294967296.0 * (4294967296.0 if frac_bits == 64 else 1.0)))
                 if frac_bits == 64:
                     f = _frac64(t[1, 1])
-                cands.append((a, f % mod, (positions, turns)))
+                cands.append((a, f % mod, [(positions, turns)]))
                 continue
         rest.append((positions, turns))
+    # several terms on the same pair of positions (CZ twice, CP after CP) are ONE rung of a ladder:
+    # their angles add (a ladder's mask can hold a partner position only once)
+    merged = {}
+    for a, f, orig in cands:
+        if a in merged:
+            merged[a] = (a, (merged[a][1] + f) % mod, merged[a][2] + orig)
+        else:
+            merged[a] = (a, f, orig)
+    cands = list(merged.values())
     muls = []
     cands.sort(key=lambda c: c[0])
 
@@ -1113,7 +1122,7 @@ def _fit_multipliers(terms, regpos, frac_bits):
             ids = {id(c) for c in group}
             cands = [c for c in cands if id(c) not in ids]
         else:
-            rest.append(cands[0][2])
+            rest.extend(cands[0][2])
             cands = cands[1:]
     return muls, rest
 

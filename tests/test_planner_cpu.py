@@ -463,3 +463,77 @@ def test_planner_streams_steps_in_order():
     steps, need = Planner(PlanConfig(18, T=11, r=4), [17 - q for q in range(18)]).plan(ops, on_step=seen.append)
     assert need is None and len(steps) > 1
     assert [id(s) for s in seen] == [id(s) for s in steps]
+
+
+def test_repeated_phase_gates_on_one_pair_add_up():
+    """Regression: two controlled phases on the same pair of qubits (CZ twice, CP after CP) are one
+    rung of a multiplier ladder with the SUM of the angles -- the ladder's mask can hold a partner
+    position only once, so they must be merged before the ladder is formed."""
+    qc = Circuit(11)
+    qc.rxx(1.206, 9, 2)
+    qc.cx(5, 8)
+    qc.h(6)
+    qc.cx(8, 0)
+    qc.cz(9, 6)
+    qc.cz(6, 9)
+    sv, _ = emulate_statevector(qc, T=9, r=3)
+    np.testing.assert_allclose(sv, ref_sim.statevector(qc, dtype=np.complex128), atol=3e-6)
+    qc = Circuit(12)
+    for q in range(12):
+        qc.h(q)
+    for a, b, th in ((1, 2, 0.785), (1, 2, 0.785), (4, 5, 3.644), (5, 4, 1.0), (7, 3, 0.1), (3, 7, 0.2), (7, 3, 0.3)):
+        qc.cp(th, a, b)
+    for q in (2, 5, 3):
+        qc.h(q)
+    for kw in ({}, {"T": 9, "r": 3}, {"T": 11, "r": 5}, {"dtype": 1}):
+        sv, _ = emulate_statevector(qc, **kw)
+        np.testing.assert_allclose(sv, ref_sim.statevector(qc, dtype=np.complex128), atol=3e-6)
+
+
+def test_random_gate_soup_against_the_oracle():
+    """A small fuzz run (the long one, ~17 000 circuits over seven geometries, found the bug above):
+    random mixes of H, CP, CX, X, RZ, U3, SWAP, CZ, RY, RXX on 9-13 qubits."""
+    import math
+
+    rng = np.random.default_rng(2024)
+    geos = [{}, {"T": 9, "r": 3}, {"T": 10, "r": 4}, {"T": 11, "r": 5}, {"T": 9, "r": 4, "L": 4}, {"dtype": 1}]
+    for case in range(60):
+        n = int(rng.integers(9, 14))
+        g = geos[case % len(geos)]
+        if g.get("T", 0) > n:
+            continue
+        qc = Circuit(n)
+        for _ in range(int(rng.integers(5, 70))):
+            k = int(rng.integers(0, 12))
+            a, b, c = (int(x) for x in rng.choice(n, size=3, replace=False))
+            if k == 0:
+                qc.h(a)
+            elif k == 1:
+                qc.cp(float(rng.uniform(0, 6.28)), a, b)
+            elif k == 2:
+                qc.cx(a, b)
+            elif k == 3:
+                qc.x(a)
+            elif k == 4:
+                qc.rz(float(rng.uniform(0, 6.28)), a)
+            elif k == 5:
+                qc.u3(*[float(x) for x in rng.uniform(0, 6.28, 3)], a)
+            elif k == 6:
+                qc.swap(a, b)
+            elif k == 7:
+                qc.cz(a, b)
+            elif k == 8:
+                qc.ry(float(rng.uniform(0, 6.28)), a)
+            elif k == 9:
+                qc.cp(math.pi / 2 ** int(rng.integers(1, 6)), a, b)
+            elif k == 10:
+                qc.h(a)
+                qc.cp(math.pi / 4, b, a)
+                qc.cp(math.pi / 8, c, a)
+            else:
+                qc.rxx(float(rng.uniform(0, 6.28)), a, b)
+        report = []
+        sv, _ = emulate_statevector(qc, report=report, **g)
+        tol = 3e-5 if g.get("dtype", 0) == 0 else 1e-11
+        np.testing.assert_allclose(sv, ref_sim.statevector(qc, dtype=np.complex128), atol=tol, err_msg=f"case {case} {g}")
+        assert all(w == 1 for _, _, w in report), (case, report)
