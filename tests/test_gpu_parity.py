@@ -350,3 +350,23 @@ def test_fresh_state_is_zero_state_whoever_looks_first():
         # ... or is written for real when the next thing is a read-out
         sv.reset()
         np.testing.assert_array_equal(sv.statevector(), want)
+
+
+def test_random_gate_soup_on_the_device(sim):
+    """Fuzz-style parity of the CUDA path: random mixes of gates (tests/soup.py: one- and two-qubit
+    gates, Toffolis with mixed control states, controlled rotations, butterflies) on 9-16 qubits,
+    several tile geometries, complex64 and complex128, against the oracle."""
+    from soup import gate_soup
+
+    rng = np.random.default_rng(77)
+    geos = [{}, {"T": 9, "r": 3}, {"T": 10, "r": 4}, {"T": 12, "r": 5}, {"T": 13, "r": 4}, {"dtype": np.complex128}, {"dtype": np.complex128, "r": 4, "T": 11}]
+    for case in range(140):
+        n = int(rng.integers(9, 17))
+        g = geos[case % len(geos)]
+        if g.get("T", 0) > n:
+            continue
+        qc = gate_soup(n, int(rng.integers(5, 90)), rng, wide=case % 2 == 1)
+        got = sim.statevector_sim(qc, **g)
+        c128 = g.get("dtype") is np.complex128
+        want = ref_sim.statevector(qc, dtype=np.complex128)
+        np.testing.assert_allclose(got, want, atol=1e-11 if c128 else 3e-5, err_msg=f"case {case} n={n} {g}")

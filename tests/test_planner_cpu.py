@@ -492,46 +492,18 @@ def test_repeated_phase_gates_on_one_pair_add_up():
 
 def test_random_gate_soup_against_the_oracle():
     """A small fuzz run (the long one, ~17 000 circuits over seven geometries, found the bug above):
-    random mixes of H, CP, CX, X, RZ, U3, SWAP, CZ, RY, RXX on 9-13 qubits."""
-    import math
+    random mixes of one- and two-qubit gates, Toffolis with mixed control states, controlled
+    rotations, QFT-like butterflies (tests/soup.py) on 9-13 qubits."""
+    from soup import gate_soup
 
     rng = np.random.default_rng(2024)
     geos = [{}, {"T": 9, "r": 3}, {"T": 10, "r": 4}, {"T": 11, "r": 5}, {"T": 9, "r": 4, "L": 4}, {"dtype": 1}]
-    for case in range(60):
+    for case in range(72):
         n = int(rng.integers(9, 14))
         g = geos[case % len(geos)]
         if g.get("T", 0) > n:
             continue
-        qc = Circuit(n)
-        for _ in range(int(rng.integers(5, 70))):
-            k = int(rng.integers(0, 12))
-            a, b, c = (int(x) for x in rng.choice(n, size=3, replace=False))
-            if k == 0:
-                qc.h(a)
-            elif k == 1:
-                qc.cp(float(rng.uniform(0, 6.28)), a, b)
-            elif k == 2:
-                qc.cx(a, b)
-            elif k == 3:
-                qc.x(a)
-            elif k == 4:
-                qc.rz(float(rng.uniform(0, 6.28)), a)
-            elif k == 5:
-                qc.u3(*[float(x) for x in rng.uniform(0, 6.28, 3)], a)
-            elif k == 6:
-                qc.swap(a, b)
-            elif k == 7:
-                qc.cz(a, b)
-            elif k == 8:
-                qc.ry(float(rng.uniform(0, 6.28)), a)
-            elif k == 9:
-                qc.cp(math.pi / 2 ** int(rng.integers(1, 6)), a, b)
-            elif k == 10:
-                qc.h(a)
-                qc.cp(math.pi / 4, b, a)
-                qc.cp(math.pi / 8, c, a)
-            else:
-                qc.rxx(float(rng.uniform(0, 6.28)), a, b)
+        qc = gate_soup(n, int(rng.integers(5, 70)), rng, wide=case % 2 == 1)
         report = []
         sv, _ = emulate_statevector(qc, report=report, **g)
         tol = 3e-5 if g.get("dtype", 0) == 0 else 1e-11
