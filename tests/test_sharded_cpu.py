@@ -81,6 +81,10 @@ def _worker(rank, world, port, case, out_dir):
 
         if case == "qft":
             qc = ghz_qft_circuit(13)
+        elif case == "soup":
+            from soup import gate_soup
+
+            qc = gate_soup(13, 120, np.random.default_rng(99), wide=True)
         elif case == "random":
             qc = random_circuit(13, 6, seed=21, two_qubit="cx")
             qc.mcx([0, 12], 6)
@@ -112,7 +116,7 @@ def _worker(rank, world, port, case, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,case", [(2, "qft"), (2, "random"), (4, "qft"), (4, "random"), (2, "big")])
+@pytest.mark.parametrize("world,case", [(2, "qft"), (2, "random"), (4, "qft"), (4, "random"), (2, "big"), (4, "soup"), (2, "soup")])
 def test_sharded_statevector_over_gloo(tmp_path, world, case):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
