@@ -370,3 +370,29 @@ def test_random_gate_soup_on_the_device(sim):
         c128 = g.get("dtype") is np.complex128
         want = ref_sim.statevector(qc, dtype=np.complex128)
         np.testing.assert_allclose(got, want, atol=1e-11 if c128 else 3e-5, err_msg=f"case {case} n={n} {g}")
+
+
+def test_random_measured_circuits_on_the_device(sim):
+    """run(): random gate soups with terminal measurements of a random subset of qubits, some with a
+    mid-circuit measurement and a reset in between (rewritten into CX onto fresh qubits,
+    circuit_preprocessing.py:729-836); the outcome labels must be identical to the oracle's and
+    the probabilities agree to 1e-5."""
+    from soup import gate_soup
+
+    rng = np.random.default_rng(4242)
+    for case in range(30):
+        n = int(rng.integers(3, 11))
+        qc = gate_soup(n, int(rng.integers(3, 40)), rng, wide=case % 2 == 0) if n >= 3 else Circuit(n)
+        if case % 3 == 0:
+            q = int(rng.integers(0, n))
+            qc.measure(q)
+            if case % 6 == 0:
+                qc.reset(q)
+            tail = gate_soup(n, int(rng.integers(2, 15)), rng)
+            qc.data.extend(tail.data)
+        qubits = sorted(int(x) for x in rng.choice(n, size=int(rng.integers(1, n + 1)), replace=False))
+        qc.measure(qubits)
+        got = sim.run(qc, None)
+        want = ref_sim.run(qc, None)
+        assert set(got) == set(want), (case, sorted(set(got) ^ set(want))[:5])
+        assert max(abs(got[k] - want[k]) for k in got) < 1e-5, case
