@@ -32,7 +32,7 @@ import numpy as np
 METRIC = "statevector_gates_per_s"
 UNIT = "gates/s"
 LOCAL_QUBITS = 30
-CPU_SAMPLE_QUBITS = 26
+CPU_SAMPLE_QUBITS = int(os.environ.get("QB2_CPU_SAMPLE_QUBITS", 26))  # (tests shrink it)
 E2E_SHOTS = 4096
 
 

@@ -509,3 +509,25 @@ def test_random_gate_soup_against_the_oracle():
         tol = 3e-5 if g.get("dtype", 0) == 0 else 1e-11
         np.testing.assert_allclose(sv, ref_sim.statevector(qc, dtype=np.complex128), atol=tol, err_msg=f"case {case} {g}")
         assert all(w == 1 for _, _, w in report), (case, report)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: one JSON line with the keys of the bench contract (the CPU arm runs
+    without a GPU; the sample register is shrunk here to keep the test short)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QB2_CPU_SAMPLE_QUBITS="16")
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
