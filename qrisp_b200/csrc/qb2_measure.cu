@@ -145,7 +145,25 @@ __global__ void __launch_bounds__(SAMPLE_THREADS)
     for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
         const vec *src = state + (c << cb);
         double acc = 0;
-        for (uint32_t i = threadIdx.x; i < csize; i += SAMPLE_THREADS) acc += abs2(__ldcs(src + i));
+        if constexpr (sizeof(vec) == 8) {
+            // complex64: two amplitudes per 16-byte load, four loads in flight per thread (same double
+            // arithmetic per amplitude as abs2(): the draw kernel re-adds the same numbers)
+            auto two = [](const float4 v) {
+                return (double)v.x * (double)v.x + (double)v.y * (double)v.y + ((double)v.z * (double)v.z + (double)v.w * (double)v.w);
+            };
+            const float4 *src4 = reinterpret_cast<const float4 *>(src);
+            const uint32_t n4 = csize >> 1;
+            uint32_t i = threadIdx.x;
+            for (; i + 3 * SAMPLE_THREADS < n4; i += 4 * SAMPLE_THREADS) {
+                const float4 a = __ldcs(src4 + i), b = __ldcs(src4 + i + SAMPLE_THREADS),
+                             c4 = __ldcs(src4 + i + 2 * SAMPLE_THREADS), d = __ldcs(src4 + i + 3 * SAMPLE_THREADS);
+                acc += (two(a) + two(b)) + (two(c4) + two(d));
+            }
+            for (; i < n4; i += SAMPLE_THREADS) acc += two(__ldcs(src4 + i));
+            if (csize == 1u && threadIdx.x == 0) acc = abs2(__ldcs(src));
+        } else {
+            for (uint32_t i = threadIdx.x; i < csize; i += SAMPLE_THREADS) acc += abs2(__ldcs(src + i));
+        }
         const double t = block_sum(acc, sh);
         if (threadIdx.x == 0) sums[c] = t;
     }
