@@ -62,10 +62,14 @@ class DeviceOps:
             self._fresh = False
         _lib.check(
             self.lib.qb2_run_pass(
-                self.state.data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream()
+                self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream()
             ),
             "qb2_run_pass",
         )
+
+    def _raw_state(self):
+        """The amplitude buffer as it is (a pass may run on a fresh state without the zeros written)."""
+        return self.state
 
     def _materialize(self):
         """Write |0...0> for real if it is still pending (see :meth:`StateVector.reset`)."""
@@ -119,19 +123,33 @@ class StateVector(DeviceOps):
         self.cfg = PlanConfig(self.n, self.dtype, T=T, r=r, L=L)
         self.pos = [self.num_qubits - 1 - q for q in range(self.num_qubits)] + list(range(self.num_qubits, self.n))
         self.hi_base = 0
-        self.state = torch.empty(2 << self.n, dtype=real, device=self.device)
+        self._buf = torch.empty(2 << self.n, dtype=real, device=self.device)
         self._scratch = None
         self.stats = {"passes": 0, "kernel_ops": 0, "gate_ops": 0, "phases": 0, "big": 0}
         self.io = {"h2d": 0, "d2h": 0}  # bytes copied between host and device
         self.reset()
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def state(self):
+        """The amplitude buffer (torch tensor of 2 * 2**n reals).  Looking at it writes a pending
+        |0...0> first (see :meth:`reset`)."""
+        self._materialize()
+        return self._buf
+
+    @state.setter
+    def state(self, buf):
+        self._buf = buf
+
+    def _raw_state(self):
+        return self._buf
+
     def _stream(self):
         return ctypes.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
 
     def _scratch_buf(self):
         if self._scratch is None:
-            self._scratch = _torch().empty_like(self.state)
+            self._scratch = _torch().empty_like(self._buf)
         return self._scratch
 
     def reset(self):
@@ -141,7 +159,7 @@ class StateVector(DeviceOps):
         self._fresh = True
 
     def _init_basis(self):
-        _lib.check(self.lib.qb2_init_basis(self.state.data_ptr(), self.n, 0, self.dtype, self._stream()), "qb2_init_basis")
+        _lib.check(self.lib.qb2_init_basis(self._buf.data_ptr(), self.n, 0, self.dtype, self._stream()), "qb2_init_basis")
 
     def synchronize(self):
         _torch().cuda.current_stream(self.device).synchronize()

@@ -335,6 +335,9 @@ def test_fresh_state_is_zero_state_whoever_looks_first():
         sv = StateVector(n)
         np.testing.assert_array_equal(sv.statevector(), want)
         sv = StateVector(n)
+        raw = sv.state.cpu().numpy().view(np.complex64)  # the public buffer attribute writes the zeros too
+        assert raw[0] == 1 and not raw[1:].any()
+        sv = StateVector(n)
         assert abs(sv.norm2() - 1.0) < 1e-12
         sv = StateVector(n)
         p = sv.probabilities(list(range(min(n, 10))))
