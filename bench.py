@@ -260,15 +260,11 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     # ---- compile once: the timed region replays the resident program
-    canonical_pos = list(sv.pos)
     prog = sv.compile(instrs)
-    final_pos = list(sv.pos)
 
     def step():
         sv.reset()
-        sv.pos[:] = canonical_pos
         prog.run()
-        sv.pos[:] = final_pos
 
     # the clock sampler streams from before the warm-up (nvidia-smi takes a moment to start); the
     # samples that fall inside the timed region are picked out by line count below
@@ -288,11 +284,9 @@ def run_gpu_arm(args):
     marks = []
     for k in range(args.steps):
         sv.reset()
-        sv.pos[:] = canonical_pos
         ev[2 * k].record()
         prog.run()
         ev[2 * k + 1].record()
-        sv.pos[:] = final_pos
     ev_end.record()
     barrier()
     launches = int(lib.qb2_launch_count())
@@ -315,9 +309,7 @@ def run_gpu_arm(args):
     if world > 1:
         # one extra, untimed replay with events around every qubit swap
         sv.reset()
-        sv.pos[:] = canonical_pos
         prog.run(time_comm=True)
-        sv.pos[:] = final_pos
         c = torch.tensor([prog.comm_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.MAX)
         comm_ms = float(c[0])
@@ -332,17 +324,20 @@ def run_gpu_arm(args):
     per_pass_ms = None
     if world == 1:
         sv.reset()
-        sv.pos[:] = canonical_pos
+        prog._enter()
         pev = []
         for i in range(len(prog.steps)):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             s_, o_, h_ = prog.steps[i], prog.offsets[i], prog._headers[i]
-            sv._run_pass(s_, h_, prog.dev, o_) if s_.kind == "pass" else sv._run_big(s_)
+            if s_.kind == "pass":
+                sv._run_pass(s_, h_, prog.dev, o_, sparse=prog._entry_sparse if i == 0 else None)
+            else:
+                sv._run_big(s_)
             e1.record()
             pev.append((e0, e1))
         torch.cuda.synchronize()
-        sv.pos[:] = final_pos
+        sv.pos[:] = prog.pos_out
         per_pass_ms = [round(a.elapsed_time(b), 3) for a, b in pev]
     roofline = {
         "kernel": "pass_kernel<float,RB=5,256,2,lean>: packed FP32x2 arithmetic, 2 CTAs x 256 threads per SM, 32 amplitudes per thread",

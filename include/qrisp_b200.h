@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QB2_ABI_VERSION 6
+#define QB2_ABI_VERSION 7
 
 #define QB2_C64 0
 #define QB2_C128 1
@@ -63,6 +63,28 @@ int qb2_stream_sync(void *stream);
  * not hold the basis state passes QB2_NO_BASIS. */
 #define QB2_NO_BASIS UINT64_MAX
 int qb2_init_basis(void *state, int n, uint64_t basis, int dtype, void *stream);
+/* All amplitudes zero except the `count` listed ones: state[idx_dev[i]] = amp_dev[i] (device arrays; local
+ * physical indices, amplitudes in the state's dtype).  The dense form of a state that qb2_sparse_prefix
+ * evolved on the host. */
+int qb2_init_sparse(void *state, int n, const uint64_t *idx_dev, const void *amp_dev, uint32_t count, int dtype,
+                    void *stream);
+
+/* ---------------------------------------------------------------- sparse start (host only, no device work)
+ * replaces the reference's sparse start of a simulation: TensorFactor keeps a fresh qubit as a sparse
+ * BiArray and contracts gates sparsely while the state has few non-zero amplitudes
+ * (tensor_factor.py:32-50, :86-89; bi_arrays.py:1197-1213).  Here the unitary instructions
+ * 0 .. n_instr-1 are applied, in order, to a list of non-zero amplitudes for as long as the list stays
+ * within `max_support` entries; the first instruction that would outgrow it stops the walk and is NOT
+ * applied.  The dense sweep then starts from the list (QB2_FEATURE_ZERO_INPUT / qb2_init_sparse).
+ *   instruction i acts on qubits qidx[qoff[i] .. qoff[i+1]) (qubits[0] = most significant bit of its matrix
+ *   index, the reference's convention: tensor_factor.py:79-89) with the row-major complex128 matrix at
+ *   mat + 2 * moff[i] (interleaved re, im).
+ *   idx / amp / count: the list, in and out (capacity max_support; bit q of an index = value of qubit q;
+ *   amp interleaved re, im); entries smaller than drop_tol in modulus are dropped; sorted by index.
+ *   consumed: number of instructions applied. */
+int qb2_sparse_prefix(int n_instr, const int32_t *qoff, const int32_t *qidx, const int64_t *moff, const double *mat,
+                      uint32_t max_support, double drop_tol, uint64_t *idx, double *amp, uint32_t *count,
+                      int32_t *consumed);
 
 /* ---------------------------------------------------------------- gate application
  * qb2_run_pass: the fused multi-gate pass.  Replaces QuantumState.apply_operation /
@@ -85,9 +107,17 @@ int qb2_init_basis(void *state, int n, uint64_t basis, int dtype, void *stream);
  * `blob_dev` is the whole packed pass on the device (256-byte aligned; only its phase tables
  * are read there).  `hi_base` holds the bits of the physical index at
  * positions >= n (the rank bits of a sharded state; 0 on one GPU).
+ *
+ * `sparse_dev` / `n_sparse`: only read when the caller's copy of the header has QB2_FEATURE_ZERO_INPUT set:
+ * the state buffer has not been written since the reset and the pass builds its input from this list of
+ * non-zero amplitudes (device memory, 16-byte aligned): uint32 tile[n_sparse] (ascending tile numbers:
+ * the tile's non-tile bits gathered through header.seg), uint32 loc[n_sparse] ((thread << r) | register
+ * under the first phase's distribution), each array padded to a multiple of 16 bytes, then n_sparse
+ * amplitudes in the pass dtype.  |0...0> on rank 0 is the one-entry list {0, 0, 1}; n_sparse = 0 is the
+ * all-zero shard of another rank.  Tiles without an entry are stored as zeros without running the ops.
  */
 int qb2_run_pass(void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev, int dtype,
-                 void *stream);
+                 void *stream, const void *sparse_dev, uint32_t n_sparse);
 
 /* Dense k-qubit matrix with k larger than a pass can hold in registers (k <= 10): the
  * correctness path for big fused unitaries.  Out of place: dst != src.  `matrix_dev`:
@@ -144,13 +174,17 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 /* a pass that contains QB2_OP_MAT2/3/4 or the general QB2_OP_DIAG needs the full kernel; all
  * other passes run a leaner one (smaller instruction footprint) */
 #define QB2_FEATURE_FULL 1u
-/* phase 0 keeps tile positions 0..3 on thread bits 0..3 (one 128-byte line per 16 lanes) and the
- * pass has the `pf` table: the kernel may fetch tiles with bulk async copies into shared
- * memory, one tile ahead of the one being processed */
-#define QB2_FEATURE_PREFETCH 2u /* reserved */
-#define QB2_FEATURE_ZERO_INPUT 4u /* set by the caller in its copy of the header: the state is |0...0> and has not
-                                     been written yet -- the pass does not read it (amplitude 1 at global index
-                                     0, else 0) and so also does the work of qb2_init_basis */
+/* complex64, T = 13, r = 5, tile positions 0..3 plus at most three runs (of at most 8 bits) of higher ones: the
+ * tile is one box of a rank-5 tensor map and the pass may run on the TMA kernel (one cp.async.bulk.tensor
+ * load and one bulk tensor store per tile, see qb2_pass_tma.cuh).  Phase 0's xw / xr / xflags then hold the
+ * slot maps of the 128B-swizzled tile buffers: xr = where the FIRST phase's distribution finds its
+ * amplitudes in the buffer the load fills, xw = where the LAST phase's distribution puts them for the
+ * store.  Tile index bit i (i-th lowest tile position) has column 1<<i, bits 4..6 additionally 1<<(i-3). */
+#define QB2_FEATURE_TMA 2u
+#define QB2_FEATURE_ZERO_INPUT 4u /* set by the caller in its copy of the header: the state buffer has not been
+                                     written since the reset -- the pass does not read it; its input is the list
+                                     of non-zero amplitudes handed to qb2_run_pass (|0...0>: one entry) */
+#define QB2_MAX_SPARSE 1024 /* entries of that list */
 
 #define QB2_OP_MAT1 1 /* 2x2 on register bit b0 */
 #define QB2_OP_MAT2 2 /* 4x4 on register bits b0 < b1 (matrix index bit 0 <-> b0) */
@@ -213,6 +247,7 @@ int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, cons
 #define QB2_IO_OFFSET 128
 #define QB2_CODE_DBITS 141   /* this record and the following ones are DIAG_BIT ops with flags & 1 and a slot, one per
                                 register bit set in `tab` of this record, in descending bit order: run as one op */
+#define QB2_CODE_END 148     /* first unused code */
 #define QB2_CODE_CXL 142     /* + index of (top, length) in (2,2),(3,2),(3,3),(4,2),(4,3),(4,4): this record and the
                                 next length-1 are X on register bit top-k-1 controlled by register bit top-k
                                 (k = 0, 1, ...), no other controls: a CX chain inside the registers, one op */
@@ -244,7 +279,7 @@ typedef struct qb2_pass_header { /* 128 bytes */
     uint32_t tab_off;    /* phase tables, after the small section: uint32 (C64) / uint64 (C128) */
     uint32_t n_ops;
     uint32_t features; /* QB2_FEATURE_*: which kernel variant the pass needs */
-    uint16_t pf;       /* reserved (0) */
+    uint16_t rsv16;    /* 0 */
     uint16_t n_slots;  /* phase slots used by the pass (see qb2_op.b1), at most QB2_MAX_SLOTS */
     qb2_seg seg[QB2_MAX_SEGS];
 } qb2_pass_header;
@@ -254,7 +289,8 @@ typedef struct qb2_phase { /* 32 bytes */
     uint32_t n_ops;
     uint32_t pcol; /* index into the u64 area: uint64[T-r], physical offset of thread bit b */
     uint32_t rphys; /* index into the u64 area: uint64[2**r], physical offset of register j */
-    /* exchange that ENTERS this phase (unused for phase 0); indices into the u16 area:
+    /* exchange that ENTERS this phase (phase 0: the tile buffers of the TMA kernel, see QB2_FEATURE_TMA; unused
+     * otherwise); indices into the u16 area:
      * uint16[(T-r) + 2**r] each: shared-memory slot = XOR of the columns of the set thread
      * bits, XOR the register entry. */
     uint32_t xw; /* slot map under the PREVIOUS phase's distribution (store side) */

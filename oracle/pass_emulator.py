@@ -32,6 +32,8 @@ def parse(blob):
     assert magic == MAGIC and total == len(b), (hex(magic), total, len(b))
     P = ParsedPass()
     P.n, P.T, P.r, P.dtype, P.small, P.n_slots = n, T, r, dtype, small, n_slots
+    P.features = _features
+    assert _pf == 0, "header.rsv16"
     P.segs = [struct.unpack_from("<BBBB", b, 64 + 4 * i)[:3] for i in range(n_seg)]
     P.phases = [struct.unpack_from("<8I", b, phases_off + 32 * i)[:7] for i in range(n_phases)]
     P.ops = []
@@ -155,9 +157,66 @@ def _phase(turns, dtype):
     return np.exp(1j * ang)
 
 
-def run(blob, state, hi_base=0, report=None):
-    """Apply the pass to ``state`` (complex numpy array of 2**n, modified copy returned)."""
+def tma_slot(t):
+    """Slot (amplitudes) of tile index ``t`` in a buffer written by a bulk tensor copy with the 128-byte
+    swizzle (CU_TENSOR_MAP_SWIZZLE_128B): 128-byte rows, 16-byte chunk c of row r sits at chunk c ^ (r & 7)."""
+    t = np.asarray(t, dtype=np.int64)
+    row, chunk, half = t >> 4, (t >> 1) & 7, t & 1
+    return row * 16 + ((chunk ^ (row & 7)) << 1) + half
+
+
+def check_tma_maps(P, report=None):
+    """QB2_FEATURE_TMA: phase 0's xr / xw maps must send every (thread, register) of the first / last
+    phase to the slot the tensor map's box order + swizzle gives its tile index; the tile must be
+    expressible as a rank-5 box (positions 0..3, at most three runs of at most 8 higher positions)."""
+    T, r = P.T, P.r
+    NR, TB = 1 << r, T - r
+    assert P.dtype == 0 and T == 13 and r == 5
+    nontile = set()
+    for src, dst, ln in P.segs:
+        nontile.update(range(dst, dst + ln))
+    tile_pos = [x for x in range(P.n) if x not in nontile]
+    assert len(tile_pos) == T and tile_pos[:4] == [0, 1, 2, 3]
+    dims, i, high = 0, 0, tile_pos[4:]
+    while i < len(high):
+        j = i
+        while j + 1 < len(high) and high[j + 1] == high[j] + 1 and j + 1 - i < 8:
+            j += 1
+        dims += 1
+        i = j + 1
+    assert dims <= 3, "tile needs more than three box dimensions"
+    rank = {x: i for i, x in enumerate(tile_pos)}
+    tid = np.arange(1 << TB, dtype=np.int64)
+    first_op, nops, pcol0, rphys0, xw, xr, xflags = P.phases[0]
+    for side, ph, m, flag, sh in (("load", P.phases[0], xr, 2, 16), ("store", P.phases[-1], xw, 1, 8)):
+        pcol, rphys = ph[2], ph[3]
+        tix = np.zeros((1 << TB, NR), dtype=np.int64)  # tile index of (thread, register)
+        for b in range(TB):
+            x = int(P.a64[pcol + b]).bit_length() - 1
+            tix += (((tid >> b) & 1) << rank[x])[:, None]
+        for j in range(NR):
+            v = int(P.a64[rphys + j])
+            tix[:, j] += sum(1 << rank[x] for x in range(64) if (v >> x) & 1)
+        want = tma_slot(tix)
+        tb = np.zeros(1 << TB, dtype=np.int64)
+        for b in range(TB):
+            tb[((tid >> b) & 1).astype(bool)] ^= int(P.a16[m + b])
+        rreg = P.a16[m + TB : m + TB + NR].astype(np.int64)
+        got = tb[:, None] ^ rreg[None, :]
+        assert np.array_equal(got, want), f"TMA {side} map does not match the swizzled box layout"
+        if xflags & flag:
+            k = (xflags >> sh) & 0xFF
+            assert np.array_equal(rreg, np.arange(NR) << k) and not np.any(tb & ((NR - 1) << k))
+            assert k in (7, 8)
+        _check_conflicts(got, 16, report, "tma-" + side, 0)
+
+
+def run(blob, state, hi_base=0, report=None, sparse=None):
+    """Apply the pass to ``state`` (complex numpy array of 2**n, modified copy returned).  ``sparse``:
+    the (tile, loc, amp) list of QB2_FEATURE_ZERO_INPUT -- the state is then not read."""
     P = parse(blob)
+    if P.features & 2:
+        check_tma_maps(P, report)
     n, T, r = P.n, P.T, P.r
     NR, TB = 1 << r, T - r
     nthreads = 1 << TB
@@ -189,6 +248,16 @@ def run(blob, state, hi_base=0, report=None):
         addr = xloc[:, None] | (P.io[:NR] // np.uint64(csize))[None, :]
         load_addr = addr.astype(np.int64)
         regs = state[addr.astype(np.int64)]  # [thread, j]
+        if sparse is not None:
+            sp_tile, sp_loc, sp_amp = sparse
+            assert np.all(np.diff(sp_tile.astype(np.int64)) >= 0), "sparse list must be sorted by tile"
+            regs = np.zeros_like(regs)
+            hit = np.flatnonzero(sp_tile == t)
+            for e in hit:
+                regs[int(sp_loc[e]) >> r, int(sp_loc[e]) & (NR - 1)] = sp_amp[e]
+            if len(hit) == 0:
+                state[addr.astype(np.int64)] = 0  # the kernel stores zeros without running the ops
+                continue
         seen = np.zeros(1 << T, dtype=bool)
         for pi, (first_op, nops, pcol, rphys, xw, xr, xflags) in enumerate(P.phases):
             if pi > 0:

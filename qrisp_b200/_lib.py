@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libqb2.so")
 
-QB2_ABI_VERSION = 6
+QB2_ABI_VERSION = 7
 QB2_C64, QB2_C128 = 0, 1
 QB2_NO_BASIS = (1 << 64) - 1
 
@@ -31,9 +31,15 @@ SYMBOLS = {
     "qb2_memcpy_d2h": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "qb2_stream_sync": (_c.c_int, [_c.c_void_p]),
     "qb2_init_basis": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_int, _c.c_void_p]),
+    "qb2_init_sparse": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_int, _c.c_void_p]),
+    "qb2_sparse_prefix": (
+        _c.c_int,
+        [_c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_double, _c.c_void_p, _c.c_void_p,
+         _c.POINTER(_c.c_uint32), _c.POINTER(_c.c_int32)],
+    ),
     "qb2_run_pass": (
         _c.c_int,
-        [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p],
+        [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32],
     ),
     "qb2_apply_matrix_big": (
         _c.c_int,

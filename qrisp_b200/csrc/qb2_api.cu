@@ -27,17 +27,18 @@ int check_cuda(cudaError_t e, const char *what) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-            cached = sms;
+int sm_count() {  // of the CURRENT device (cached per device ordinal)
+    static int cached[QB2_MAX_DEVICES] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= QB2_MAX_DEVICES) return 148;
+    if (cached[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            cached[dev] = sms;
         else
             return 148;
     }
-    return cached;
+    return cached[dev];
 }
 
 static int check_dtype(int dtype, const char *who) {
@@ -99,11 +100,17 @@ int qb2_init_basis(void *state, int n, uint64_t basis, int dtype, void *stream) 
     return launch_init_basis(state, n, basis, dtype, (cudaStream_t)stream);
 }
 
+int qb2_init_sparse(void *state, int n, const uint64_t *idx_dev, const void *amp_dev, uint32_t count, int dtype,
+                    void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_init_sparse")) return rc;
+    return launch_init_sparse(state, n, idx_dev, amp_dev, count, dtype, (cudaStream_t)stream);
+}
+
 int qb2_run_pass(void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev, int dtype,
-                 void *stream) {
+                 void *stream, const void *sparse_dev, uint32_t n_sparse) {
     if (int rc = check_dtype(dtype, "qb2_run_pass")) return rc;
     return launch_pass(state, n, hi_base, reinterpret_cast<const qb2_pass_header *>(header), blob_dev, dtype,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, sparse_dev, n_sparse);
 }
 
 int qb2_apply_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev,

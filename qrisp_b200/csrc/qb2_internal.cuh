@@ -38,9 +38,41 @@ int sm_count();
         if (_rc != QB2_OK) return _rc;                   \
     } while (0)
 
+#define QB2_MAX_DEVICES 64
+
+// sparse input of the first pass after a reset (QB2_FEATURE_ZERO_INPUT): the listed non-zero amplitudes,
+// sorted by tile number; `loc` = (thread << r) | register under the FIRST phase's distribution
+struct SparseInput {
+    const uint32_t *tile;  // [count] ascending tile numbers
+    const uint32_t *loc;   // [count]
+    const void *amp;       // [count] amplitudes in the pass dtype
+    uint32_t count;
+};
+
+struct PassLaunch {
+    void *state;
+    uint64_t hi_base;
+    const qb2_pass_header *h;
+    const void *blob_dev;
+    uint32_t ntiles;
+    cudaStream_t s;
+    SparseInput sparse;
+};
+
+// one translation unit per kernel variant (qb2_pass_inst.cu compiled with -DQB2_INST=k, see Makefile):
+// k = 2 * geometry + full; geometries in the order of qb2_pass.cu's table; 12, 13: the TMA kernel
+#define QB2_N_PASS_VARIANTS 14
+#define QB2_DECLARE_VARIANT(k) int launch_pass_variant_##k(const PassLaunch &L);
+QB2_DECLARE_VARIANT(0) QB2_DECLARE_VARIANT(1) QB2_DECLARE_VARIANT(2) QB2_DECLARE_VARIANT(3) QB2_DECLARE_VARIANT(4)
+QB2_DECLARE_VARIANT(5) QB2_DECLARE_VARIANT(6) QB2_DECLARE_VARIANT(7) QB2_DECLARE_VARIANT(8) QB2_DECLARE_VARIANT(9)
+QB2_DECLARE_VARIANT(10) QB2_DECLARE_VARIANT(11) QB2_DECLARE_VARIANT(12) QB2_DECLARE_VARIANT(13)
+#undef QB2_DECLARE_VARIANT
+
 // launchers implemented per translation unit
 int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, int dtype,
-                cudaStream_t s);
+                cudaStream_t s, const void *sparse_dev, uint32_t n_sparse);
+int launch_init_sparse(void *state, int n, const uint64_t *idx_dev, const void *amp_dev, uint32_t count, int dtype,
+                       cudaStream_t s);
 int launch_init_basis(void *state, int n, uint64_t basis, int dtype, cudaStream_t s);
 int launch_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev, const int *targets,
                       int k, uint64_t cmask, uint64_t cval, int dtype, cudaStream_t s);

@@ -1,0 +1,370 @@
+// qb2_pass_tma.cuh -- the TMA pass kernel (complex64, T = 13 tile bits, r = 5 register bits).
+//
+// Same pass format and the same op interpreter (qb2_pass_ops.inc) as the register-pipelined kernel of
+// qb2_pass_kernel.cuh; what differs is how a tile travels:
+//
+//   HBM --one cp.async.bulk.tensor (64 KB box, mbarrier)--> landing buffer --LDS--> registers
+//       --ops--> [group buffer exchange --ops-->]* --STS--> group buffer --one bulk tensor store--> HBM
+//
+// One CTA per SM, two compute groups of 256 threads (named barriers), three 64 KB tile buffers with the
+// 128-byte TMA swizzle: the landing buffer is being filled with the next tile while both groups compute,
+// and each group's buffer (exchanges, then source of the store) drains to HBM while the group works on
+// its next tile.  Loads and stores cost the compute warps no issue slots and no address arithmetic, and
+// no warp ever waits on a global load.
+//
+// A tile is any set of 13 index bits that contains bits 0..3 (whole 128-byte lines).  The tensor map
+// (host: make_tile_map) has dim0 = bits 0..3, a "base" dimension of box size 1 whose coordinate carries
+// all non-tile bits of the tile's address, and one dimension (stride 2**p amplitudes) per run of tile bits
+// p.. -- up to three runs of at most 8 bits.  In shared memory the box is 512 rows of 128 bytes, 16-byte
+// chunk c of row r stored at chunk c ^ (r & 7); the host expresses that as XOR columns (phase 0's xr / xw
+// maps of the pass), the same form every exchange uses.
+#pragma once
+#include <cuda.h>  // CUtensorMap and the encoder's prototype; the entry point comes from cudaGetDriverEntryPoint
+
+#include "qb2_pass_common.cuh"
+
+namespace qb2 {
+namespace {
+
+constexpr int TMA_T = 13;
+constexpr int TMA_GROUP = 256;
+constexpr uint32_t TMA_TILE_BYTES = 8u << TMA_T;
+constexpr int TMA_WIN = 1024;  // shared-window address of the dynamic shared memory: the driver's reserved 1 KB comes first
+constexpr uint32_t TMA_AUX_BYTES = 232448u - 3u * TMA_TILE_BYTES - 1024u;  // what is left of 227 KB (1 KB kept free)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// rank-5 tile copies; only coordinate 1 (the base dimension) is ever non-zero
+__device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *m, uint64_t *bar, int base) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %3, %3, %3}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(0), "r"(base) : "memory");
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap *m, const void *src, int base) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %2, %2, %2}], [%1];"
+                 ::"l"(m), "r"(smem_u32(src)), "r"(0), "r"(base) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void group_bar(uint32_t g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1u), "n"(TMA_GROUP) : "memory"); }
+
+template <bool FULL>
+__global__ void __launch_bounds__(2 * TMA_GROUP, 1)
+    pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, const uint32_t *__restrict__ tables, const uint64_t hi_base,
+                    const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off, const uint32_t sp_off,
+                    const SparseInput SP, const __grid_constant__ PassParams P) {
+    using real = float;
+    using vec = float2;
+    using frac = uint32_t;
+    using C = Cx<real>;
+    using amp = typename C::amp;
+    constexpr int RB = 5;
+    constexpr int NR = 1 << RB;
+    constexpr int TB = TMA_T - RB;
+    // dynamic shared memory: the three tile buffers first (the 128B swizzle pattern repeats every 1 KB, so they
+    // sit at the 1 KB-aligned start of the window), the descriptors' working data behind them.  Tile
+    // accesses are smem[offset] with the buffer's offset folded into the per-thread slot offset: the
+    // base of the array is an immediate of the LDS / STS, not an add per access.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *const aux = smem + 3u * TMA_TILE_BYTES;
+
+    const uint32_t g = threadIdx.x >> 8;     // compute group
+    const uint32_t tid = threadIdx.x & 255u;  // thread of the group
+    constexpr uint32_t nthreads = TMA_GROUP;
+    if (smem_u32(smem) != (uint32_t)TMA_WIN) __trap();  // (the launcher has checked the reserved size: cannot happen)
+    vec *const roots = reinterpret_cast<vec *>(aux);
+    for (uint32_t i = threadIdx.x; i < NROOT; i += blockDim.x) {
+        float s, c;
+        sincospif((float)i * (2.0f / NROOT), &s, &c);
+        roots[i] = make_float2(c, s);
+    }
+    uint64_t *const full_bar = reinterpret_cast<uint64_t *>(aux + NROOT * sizeof(vec));  // [2]: one per group
+
+    const uint8_t *const pb = reinterpret_cast<const uint8_t *>(&P);
+    const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(pb);
+    const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(pb + H->phases_off);
+    const qb2_op *const ops = reinterpret_cast<const qb2_op *>(pb + H->ops_off);
+    const real *const coefs = reinterpret_cast<const real *>(pb + H->coef_off);
+    const uint16_t *const a16 = reinterpret_cast<const uint16_t *>(pb + H->u16_off);
+    const uint64_t *const a64 = reinterpret_cast<const uint64_t *>(pb + H->u64_off);
+    const qb2_tab *const tabs = reinterpret_cast<const qb2_tab *>(pb + H->tabdesc_off);
+    const uint32_t n_phases = H->n_phases;
+    const int n_seg = H->n_seg;
+
+    uint8_t *const landing = smem;                              // buffer 0
+    const uint32_t gofs = (1u + g) * TMA_TILE_BYTES;            // this group's buffer: 1 or 2
+    uint8_t *const gbuf = smem + gofs;
+
+    // ---- per-thread context of every phase (the two groups share it): low 32 bits of the thread's physical
+    // offset | slot under the store side of the entering exchange (13 bits), slot under its load side
+    // (13 bits), bits 32.. of the offset (6 bits).  Phase 0's slots are those of the landing buffer (load
+    // side) and of the final store (store side, under the LAST phase's distribution).
+    uint2 *const ctx = reinterpret_cast<uint2 *>(aux + ctx_off);
+    if (g == 0) {
+        for (uint32_t p = 0; p < n_phases; ++p) {
+            const qb2_phase &ph = phases[p];
+            uint64_t xt = 0;
+            uint32_t wb = 0, rb = 0;
+            for (int b = 0; b < TB; ++b)
+                if ((tid >> b) & 1u) {
+                    xt |= a64[ph.pcol + b];
+                    wb ^= a16[ph.xw + b];
+                    rb ^= a16[ph.xr + b];
+                }
+            ctx[p * nthreads + tid] = make_uint2((uint32_t)xt, wb | (rb << 13) | ((uint32_t)(xt >> 32) << 26));
+        }
+    }
+    auto ctx_x = [&](const uint2 c) { return (uint64_t)(c.y >> 26) << 32 | c.x; };
+    // ---- phase slots: thread parts once per CTA (shared by the groups), tile parts once per tile and group
+    const uint32_t n_slots = H->n_slots;
+    auto two_slots = [&](const qb2_op &op) { return op.kind == QB2_OP_DIAG_BIT && !(op.flags & 1u); };
+    frac *const stile_all = reinterpret_cast<frac *>(aux + slot_off);                       // [2 groups][2][QB2_MAX_SLOTS]
+    frac *const stile = stile_all + g * 2 * QB2_MAX_SLOTS;
+    uint16_t *const slot_op = reinterpret_cast<uint16_t *>(stile_all + 4 * QB2_MAX_SLOTS);   // [QB2_MAX_SLOTS]
+    frac *const sthr = reinterpret_cast<frac *>(slot_op + QB2_MAX_SLOTS);                    // [n_slots][threads]
+    auto ladder_sum = [&](const qb2_op &op, const uint32_t which, const uint64_t x) {
+        const qb2_tab *tb = tabs + (op.kind == QB2_OP_BFLY ? (uint32_t)op.tab : (uint32_t)op.data);
+        const int nthr = op.ntab_thr, nall = nthr + op.ntab_reg;
+        const int n = (two_slots(op) && which == 0u) ? nthr : nall;
+        frac r = 0;
+        for (int i = 0; i < n; ++i) r += tab_mul<frac>(tb[i], x);
+        return r;
+    };
+    auto has_slot = [&](const qb2_op &op) {
+        return op.b1 != 0 && (op.kind == QB2_OP_BFLY || op.kind == QB2_OP_DIAG_THR || op.kind == QB2_OP_DIAG_BIT);
+    };
+    if (n_slots && g == 0) {
+        for (uint32_t p = 0; p < n_phases; ++p) {
+            uint64_t xt = 0;
+            for (int b = 0; b < TB; ++b)
+                if ((tid >> b) & 1u) xt |= a64[phases[p].pcol + b];
+            const uint64_t x = hi_base | xt;
+            const uint32_t op_end = phases[p].first_op + phases[p].n_ops;
+            for (uint32_t o = phases[p].first_op; o < op_end; ++o) {
+                const qb2_op &op = ops[o];
+                if (has_slot(op)) {
+                    const uint32_t ns = two_slots(op) ? 2u : 1u;
+                    for (uint32_t w = 0; w < ns; ++w) {
+                        sthr[(op.b1 - 1u + w) * nthreads + tid] = ladder_sum(op, w, x);
+                        if (tid == 0) slot_op[op.b1 - 1u + w] = (uint16_t)(o | (w << 15));
+                    }
+                }
+            }
+        }
+    }
+    // ---- sparse input (first pass after a reset): tile numbers of the listed amplitudes; the landing
+    // buffer is not needed for loads then and serves as the all-zero tile that empty tiles store
+    const bool zero_in = (H->features & QB2_FEATURE_ZERO_INPUT) != 0u;
+    uint32_t *const sp_tile = reinterpret_cast<uint32_t *>(aux + sp_off);
+    if (zero_in) {
+        for (uint32_t i = threadIdx.x; i < SP.count; i += blockDim.x) sp_tile[i] = SP.tile[i];
+        for (uint32_t i = threadIdx.x; i < TMA_TILE_BYTES / 16u; i += blockDim.x)
+            reinterpret_cast<uint4 *>(landing)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto tile_base = [&](uint32_t t) {
+        uint64_t tb = 0;
+        for (int s = 0; s < n_seg; ++s) {
+            const qb2_seg sg = H->seg[s];
+            tb |= (uint64_t)((t >> sg.src) & ((1u << sg.len) - 1u)) << sg.dst;
+        }
+        return tb;
+    };
+    // k-th tile of this CTA: loaded into the landing buffer for group k & 1
+    auto issue_load = [&](const uint32_t k) {
+        const uint32_t t = blockIdx.x + k * gridDim.x;
+        if (t >= ntiles) return;
+        mbar_expect_tx(&full_bar[k & 1u], TMA_TILE_BYTES);
+        tma_load_tile(landing, &tmap, &full_bar[k & 1u], (int)(tile_base(t) >> 4));
+    };
+    if (threadIdx.x == 0 && !zero_in) issue_load(0);
+
+    const uint2 c0 = ctx[tid];
+    const uint64_t xthr0 = ctx_x(c0);
+    const uint32_t land_rb = ((c0.y >> 13) & 0x1fffu) * (uint32_t)sizeof(vec);
+    const uint32_t store_wb = (c0.y & 0x1fffu) * (uint32_t)sizeof(vec);
+    const uint32_t io_xf = phases[0].xflags;
+
+    amp a[NR];
+    uint32_t kpar = 0;  // parity of this group's full barrier
+    uint32_t iter = 0;
+    for (uint32_t k = g;; k += 2u, ++iter) {
+        const uint32_t t = blockIdx.x + k * gridDim.x;
+        if (t >= ntiles) break;
+        const uint64_t tbase = tile_base(t);
+        uint64_t xloc = tbase | xthr0;
+        // ---- tile part of the slotted phases: one thread per slot
+        const uint32_t spar = (iter & 1u) * QB2_MAX_SLOTS;
+        if (n_slots) {
+            for (uint32_t sl = tid >> 5; sl < n_slots; sl += nthreads >> 5)
+                if ((tid & 31u) == 0u) {
+                    const uint32_t so = slot_op[sl];
+                    stile[spar + sl] = ladder_sum(ops[so & 0x7fffu], so >> 15, tbase);
+                }
+        }
+        bool tile_zero = false;
+        if (zero_in) {
+            tile_zero = sparse_synth<real, RB>(a, sp_tile, SP, t, tid);
+            if (n_slots) group_bar(g);
+        } else {
+            mbar_wait(&full_bar[g], kpar);
+            kpar ^= 1u;
+            // (the offsets are the same for every tile: an opaque copy keeps the compiler from hoisting 32
+            // addresses out of the tile loop and spilling them)
+            uint32_t rb_t = land_rb;
+            asm volatile("" : "+r"(rb_t));
+            smem_load_any<RB, TMA_WIN>(rb_t, (io_xf & 2u) != 0u, io_xf >> 16 & 0xffu, a16 + phases[0].xr + TB, a);
+            group_bar(g);  // the landing buffer is free again (and the slots' tile parts are visible)
+            if (tid == 0) issue_load(k + 1u);
+        }
+        // the group's buffer may still be the source of the previous tile's store
+        bool gbuf_free = false;
+        auto acquire_gbuf = [&]() {
+            if (!gbuf_free) {
+                if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                group_bar(g);
+                gbuf_free = true;
+            }
+        };
+        if (tile_zero) {
+            // every op of the pass is linear: zeros stay zeros.  One bulk store of the zero tile.
+            if (tid == 0) tma_store_tile(&tmap, landing, (int)(tbase >> 4));
+            continue;
+        }
+        for (uint32_t p = 0; p < n_phases; ++p) {
+            const qb2_phase &ph = phases[p];
+            if (p > 0) {
+                // ---- exchange through the group's buffer
+                const uint2 c = ctx[p * nthreads + tid];
+                const uint32_t cz = (c.y & 0x1fffu) * (uint32_t)sizeof(vec), cw = ((c.y >> 13) & 0x1fffu) * (uint32_t)sizeof(vec);
+                const uint32_t xf = ph.xflags;
+                acquire_gbuf();
+                smem_store_any<RB, TMA_WIN>(gofs + cz, (xf & 1u) != 0u, xf >> 8 & 0xffu, a16 + ph.xw + TB, a);
+                group_bar(g);
+                {
+                    xloc = tbase | ctx_x(c);
+                    smem_load_any<RB, TMA_WIN>(gofs + cw, (xf & 2u) != 0u, xf >> 16 & 0xffu, a16 + ph.xr + TB, a);
+                }
+                group_bar(g);
+            }
+            const uint64_t X = hi_base | xloc;
+#include "qb2_pass_ops.inc"
+        }
+        // ---- the tile goes to the group's buffer in the layout of the tensor map, then ONE bulk store
+        acquire_gbuf();
+        {
+            uint32_t wb_t = gofs + store_wb;
+            asm volatile("" : "+r"(wb_t));
+            smem_store_any<RB, TMA_WIN>(wb_t, (io_xf & 1u) != 0u, io_xf >> 8 & 0xffu, a16 + phases[0].xw + TB, a);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        group_bar(g);
+        if (tid == 0) tma_store_tile(&tmap, gbuf, (int)(tbase >> 4));
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Tensor map of a pass's tiles over the local state (see the top of this file).  Returns false when the
+// tile does not fit a rank-5 map (more than three runs of tile bits above bit 3).
+inline bool make_tile_map(CUtensorMap *tm, void *state, int n, const qb2_pass_header *h, tensor_map_encode_fn encode) {
+    bool nontile[64] = {false};
+    for (int s = 0; s < h->n_seg; ++s)
+        for (int b = 0; b < h->seg[s].len; ++b) nontile[h->seg[s].dst + b] = true;
+    for (int p = 0; p < 4; ++p)
+        if (nontile[p]) return false;
+    cuuint64_t gdim[5] = {32, 1, 1, 1, 1}, gstr[4] = {128, 128, 128, 128};
+    cuuint32_t box[5] = {32, 1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+    gdim[1] = 1ull << (n - 4);  // base dimension: 128-byte lines, box 1
+    int nd = 2;
+    for (int p = 4; p < n;) {
+        if (nontile[p]) {
+            ++p;
+            continue;
+        }
+        int q = p;
+        while (q < n && !nontile[q] && q - p < 8) ++q;
+        if (nd >= 5) return false;
+        gdim[nd] = 1ull << (n - p);
+        gstr[nd - 1] = 8ull << p;
+        box[nd] = 1u << (q - p);
+        ++nd;
+        p = q;
+    }
+    for (; nd < 5; ++nd) gstr[nd - 1] = 8ull << n;  // unused dimensions: size 1
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, state, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// QB2_ELIMIT + "tma:" message = the caller falls back to the register-pipelined kernel
+template <bool FULL>
+int launch_kernel_tma(const PassLaunch &L) {
+    auto kern = pass_kernel_tma<FULL>;
+    const qb2_pass_header *h = L.h;
+    static tensor_map_encode_fn encode = nullptr;
+    static bool attr_set[QB2_MAX_DEVICES] = {false};
+    int dev = 0;
+    QB2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= QB2_MAX_DEVICES) return set_error(QB2_ELIMIT, "device ordinal %d outside the engine's table", dev);
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+            return set_error(QB2_ELIMIT, "tma: the driver has no cuTensorMapEncodeTiled");
+        encode = reinterpret_cast<tensor_map_encode_fn>(fn);
+    }
+    const uint32_t ctx_off = NROOT * sizeof(float2) + 64u;
+    const uint32_t slot_off = ctx_off + h->n_phases * TMA_GROUP * 8u;
+    const uint32_t slot_bytes = 4u * QB2_MAX_SLOTS * 4u + QB2_MAX_SLOTS * 2u + h->n_slots * TMA_GROUP * 4u;
+    const uint32_t sp_off = (slot_off + slot_bytes + 15u) & ~15u;
+    const uint32_t sp_bytes = (h->features & QB2_FEATURE_ZERO_INPUT) ? ((L.sparse.count * 4u + 15u) & ~15u) : 0u;
+    const uint32_t aux_bytes = sp_off + sp_bytes;
+    if (aux_bytes > TMA_AUX_BYTES) return set_error(QB2_ELIMIT, "tma: descriptors need %u bytes of shared memory", aux_bytes);
+    const size_t smem = (size_t)aux_bytes + 3u * TMA_TILE_BYTES;
+    CUtensorMap tm;
+    if (!make_tile_map(&tm, L.state, (int)h->n, h, encode)) return set_error(QB2_ELIMIT, "tma: tile shape not expressible");
+    if (!attr_set[dev]) {
+        int reserved = 0;
+        QB2_CUDA(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev));
+        if (reserved != TMA_WIN) return set_error(QB2_ELIMIT, "tma: %d bytes of reserved shared memory (the kernel assumes %d)", reserved, TMA_WIN);
+        QB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+        attr_set[dev] = true;
+    }
+    uint32_t grid = (uint32_t)sm_count();
+    if (grid > L.ntiles) grid = L.ntiles;
+    PassParams params;
+    memcpy(&params, h, h->small_bytes);
+    const uint32_t *tables = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(L.blob_dev) + h->tab_off);
+    kern<<<grid, 2 * TMA_GROUP, smem, L.s>>>(tm, tables, L.hi_base, L.ntiles, ctx_off, slot_off, sp_off, L.sparse, params);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "pass_kernel_tma launch");
+}
+
+}  // namespace
+}  // namespace qb2

@@ -24,7 +24,7 @@ import os
 
 import numpy as np
 
-from . import _lib
+from . import _lib, prefix
 from .engine import MIN_QUBITS, DeviceOps, Program
 from .normalize import normalize_circuit
 from .planner import QB2_C64, QB2_C128, PlanConfig, Planner
@@ -57,7 +57,7 @@ def choose_evictions(pending, pos, n_local, g, protect):
 
 
 class ShardedStateVector(DeviceOps):
-    def __init__(self, num_qubits, group=None, dtype=np.complex64, device=None, T=None, r=None, L=4):
+    def __init__(self, num_qubits, group=None, dtype=np.complex64, device=None, T=None, r=None, L=4, tma=None, prefix_support=None):
         import torch
         import torch.distributed as dist
 
@@ -81,7 +81,9 @@ class ShardedStateVector(DeviceOps):
             self.dtype, self.np_dtype = QB2_C128, np.complex128
         else:
             raise TypeError(f"unsupported amplitude dtype {dtype}")
-        self.cfg = PlanConfig(self.n, self.dtype, T=T, r=r, L=L)
+        self.cfg = PlanConfig(self.n, self.dtype, T=T, r=r, L=L, tma=tma)
+        if prefix_support is not None:
+            self.prefix_support = prefix_support
         nq = self.num_qubits
         self.pos = [nq - 1 - q for q in range(nq)] + list(range(nq, self.n_total))
         self.hi_base = self.rank << self.n
@@ -108,17 +110,15 @@ class ShardedStateVector(DeviceOps):
         return self._scratch
 
     def reset(self):
-        """Back to |0...0>.  Lazy, like :meth:`StateVector.reset`: the first pass synthesises the
-        zeros (the one sits on rank 0); anything else that looks at the shard first writes them."""
-        self._fresh_layout = True  # |0...0> is invariant under any relabelling of the qubits (see compile_ops)
-        if getattr(self, "lazy_reset", True):
-            self._fresh = True
-        else:
-            self._init_basis()
-
-    def _init_basis(self):
-        basis = 0 if self.rank == 0 else _lib.QB2_NO_BASIS
-        _lib.check(self.lib.qb2_init_basis(self.state.data_ptr(), self.n, basis, self.dtype, self._stream()), "qb2_init_basis")
+        """Back to |0...0>.  Lazy, like :meth:`StateVector.reset`: the state is a pending list of
+        non-zero amplitudes on the host; the first pass builds its tiles from this rank's entries,
+        anything else that looks at the shard first writes them.  While the state is pending no data
+        sits in HBM, so the qubit map is still free (see :meth:`_choose_initial_layout`)."""
+        self._pending = prefix.zero_state()
+        nq = self.num_qubits
+        self.pos[:] = [nq - 1 - q for q in range(nq)] + list(range(nq, self.n_total))
+        if not getattr(self, "lazy_reset", True):
+            self._materialize()
 
     def _permute_local(self, perm):
         self._materialize()
@@ -142,15 +142,21 @@ class ShardedStateVector(DeviceOps):
 
     # ------------------------------------------------------------------ planning
     def compile(self, instructions):
+        """Host prefix on the pending sparse state, then plan with swaps (every rank computes the same)."""
+        start = getattr(self, "_pending", None)
+        instructions = self._take_prefix(list(instructions))
+        entry = getattr(self, "_pending", None)
         unit_tol = 1e-6 if self.dtype == QB2_C64 else 1e-13
         ops = normalize_circuit(instructions, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
-        return self.compile_ops(ops)
+        return self.compile_ops(ops, start=start, entry=entry)
 
-    def compile_ops(self, ops):
-        """Plan with swaps.  ``self.pos`` is advanced to the map after the program."""
-        if getattr(self, "_fresh_layout", False) and self.g > 0 and os.environ.get("QB2_NO_INITIAL_LAYOUT") is None:
+    def compile_ops(self, ops, start=None, entry=None):
+        """Plan with swaps.  Returns the program; map and state stay what they were (``run`` moves them)."""
+        pos_before = list(self.pos)
+        if getattr(self, "_pending", None) is not None and self.g > 0 and os.environ.get("QB2_NO_INITIAL_LAYOUT") is None:
+            # no data in HBM yet: the map is free.  The program's entry map is the chosen one.
             self._choose_initial_layout(ops)
-        self._fresh_layout = False
+        pos_in = list(self.pos)
         planner = Planner(self.cfg, self.pos, n_total=self.n_total)
         steps = []
         pending = list(ops)
@@ -166,7 +172,10 @@ class ShardedStateVector(DeviceOps):
             if guard > 10000:
                 raise RuntimeError("swap planning does not terminate")
             steps.append(self._plan_swap(pending, protect))
-        return ShardedProgram(self, steps)
+        prog = ShardedProgram(self, steps, pos_in=pos_in, start=start, entry=entry, pos_before=pos_before)
+        self._pending = start
+        self.pos[:] = pos_before
+        return prog
 
     def _choose_initial_layout(self, ops):
         """The state is still |0...0>, which does not care which qubit sits where: the qubits that are
@@ -320,19 +329,36 @@ def _canonical(full, pos, nq):
 class ShardedProgram(Program):
     """Passes + swaps.  Pass blobs are uploaded once; swaps run on the same stream."""
 
-    def __init__(self, sv, steps):
+    def __init__(self, sv, steps, pos_in=None, start=None, entry=None, pos_before=None):
         self._swap_steps = [s for s in steps if s.kind == "swap"]
-        super().__init__(sv, steps)
+        super().__init__(sv, steps, pos_in=pos_in, start=start, entry=entry)
+        # the map the caller has when the program starts; with a pending state the program is free to
+        # begin from another one (pos_in, see ShardedStateVector._choose_initial_layout)
+        self.pos_before = list(self.pos_in) if pos_before is None else list(pos_before)
         self.n_swaps = len(self._swap_steps)
         self.comm_ms = None
 
+    def _enter(self):
+        sv = self.sv
+        if list(sv.pos) != self.pos_before:
+            raise _lib.Qb2Error("this program was compiled against another qubit map (compile it where it runs, in order)")
+        if self.pos_before != self.pos_in:
+            if getattr(sv, "_pending", None) is None:
+                raise _lib.Qb2Error("this program chooses its own entry layout and needs a state that has not been written yet")
+            sv.pos[:] = self.pos_in
+        super()._enter()
+
     def run(self, time_comm=False):
         sv = self.sv
+        self._enter()
         comm = []
+        first = True
         for s, o, h in zip(self.steps, self.offsets, self._headers):
             if s.kind == "pass":
-                sv._run_pass(s, h, self.dev, o)
+                sv._run_pass(s, h, self.dev, o, sparse=self._entry_sparse if first else None)
+                first = False
             elif s.kind == "swap":
+                first = False
                 if time_comm:
                     import torch
 
@@ -350,6 +376,7 @@ class ShardedProgram(Program):
 
             torch.cuda.synchronize()
             self.comm_ms = sum(a.elapsed_time(b) for a, b in comm)
+        sv.pos[:] = self.pos_out
         sv.stats["passes"] += self.n_passes
         sv.stats["kernel_ops"] += self.n_kernel_ops
         sv.stats["gate_ops"] += self.n_gate_ops

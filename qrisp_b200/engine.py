@@ -13,7 +13,7 @@ import ctypes
 
 import numpy as np
 
-from . import _lib
+from . import _lib, prefix
 from .normalize import normalize_circuit
 from .planner import QB2_C64, QB2_C128, PlanConfig, Planner
 
@@ -52,47 +52,125 @@ class DeviceOps:
         self.io["h2d"] += total
         return dev
 
-    def _run_pass(self, step, header, dev, offset):
-        if getattr(self, "_fresh", False):
-            # the state is |0...0> and not written yet: the pass synthesises its input
-            # (QB2_FEATURE_ZERO_INPUT, header.features at byte 56) instead of reading 2**n zeros
+    def _guard(self):
+        """Launches go to the CURRENT device: make it this state's (two engines on two devices may
+        alternate in one process)."""
+        if self.device.type == "cuda":
+            _torch().cuda.set_device(self.device)
+
+    def _upload_bytes(self, data):
+        torch = _torch()
+        host = torch.empty(max(len(data), 16), dtype=torch.uint8, pin_memory=True)
+        host.numpy()[: len(data)] = np.frombuffer(data, dtype=np.uint8)
+        dev = host.to(self.device, non_blocking=True)
+        pinned = getattr(self, "_pinned", None)
+        if not isinstance(pinned, list):
+            pinned = self._pinned = []
+        pinned.append(host)
+        del pinned[:-64]
+        self.io["h2d"] += len(data)
+        return dev
+
+    def _pending_map(self):
+        """The qubit map a pending state is laid out by: the map at the ENTRY of the plan that is being
+        launched (the planner has already moved ``self.pos`` on by the time a step is launched)."""
+        m = getattr(self, "_entry_pos", None)
+        return self.pos if m is None else m
+
+    def _sparse_for(self, step, state):
+        """Device copy of the sparse input list of ``step`` for the pending state ``state``."""
+        idx, amp = state
+        phys = prefix.to_physical(idx, self._pending_map(), len(self.pos))
+        data, count = prefix.sparse_input_list(step, phys, amp, self.n, self.hi_base, self.np_dtype)
+        return (self._upload_bytes(data) if count else None), count
+
+    def _run_pass(self, step, header, dev, offset, sparse=None):
+        """``sparse``: a ready ``(device list, count)`` for a pass that starts from the pending state
+        (a replayed program keeps it resident); built here otherwise."""
+        sp_ptr, sp_count = None, 0
+        pending = getattr(self, "_pending", None)
+        if pending is not None:
+            # the state buffer has not been written since the reset: the pass builds its tiles from the
+            # list of non-zero amplitudes (QB2_FEATURE_ZERO_INPUT, header.features at byte 56) instead of
+            # reading 2**n zeros, and stores all-zero tiles without running the ops
+            if sparse is None:
+                sparse = self._sparse_for(step, pending)
+            self._sparse_keep = sparse
+            sp_ptr = sparse[0].data_ptr() if sparse[0] is not None else None
+            sp_count = sparse[1]
             raw = bytearray(header.raw)
             raw[56:60] = (int.from_bytes(raw[56:60], "little") | QB2_FEATURE_ZERO_INPUT).to_bytes(4, "little")
             header = ctypes.create_string_buffer(bytes(raw), len(raw))
-            self._fresh = False
+            self._pending = None
         _lib.check(
             self.lib.qb2_run_pass(
-                self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream()
+                self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream(),
+                sp_ptr, sp_count,
             ),
             "qb2_run_pass",
         )
 
     def _raw_state(self):
-        """The amplitude buffer as it is (a pass may run on a fresh state without the zeros written)."""
+        """The amplitude buffer as it is (a pass may run on a state whose zeros were never written)."""
         return self.state
 
     def _materialize(self):
-        """Write |0...0> for real if it is still pending (see :meth:`StateVector.reset`)."""
-        if getattr(self, "_fresh", False):
-            self._fresh = False
-            self._init_basis()
+        """Write the pending sparse state for real (see :meth:`StateVector.reset`)."""
+        pending = getattr(self, "_pending", None)
+        if pending is not None:
+            self._pending = None
+            self._init_sparse(pending)
+
+    def _init_sparse(self, state):
+        torch = _torch()
+        idx, amp = state
+        phys = prefix.to_physical(idx, self._pending_map(), len(self.pos))
+        if len(phys):
+            mine = (phys >> np.uint64(self.n)) == np.uint64(self.hi_base >> self.n)
+            phys, amp = phys[mine] & np.uint64((1 << self.n) - 1), amp[mine]
+        count = len(phys)
+        buf = self._raw_state()
+        if count:
+            data = phys.astype(np.uint64).tobytes()
+            pad = (len(data) + 15) // 16 * 16
+            data = data + b"\0" * (pad - len(data)) + amp.astype(self.np_dtype).tobytes()
+            dev = self._upload_bytes(data)
+            self._sparse_keep = (dev, count)
+            ip, ap = dev.data_ptr(), dev.data_ptr() + pad
+        else:
+            ip = ap = None
+        _lib.check(self.lib.qb2_init_sparse(buf.data_ptr(), self.n, ip, ap, count, self.dtype, self._stream()), "qb2_init_sparse")
+
+    def _take_prefix(self, instructions):
+        """Evolve the pending sparse state through a prefix of ``instructions`` on the host
+        (:mod:`qrisp_b200.prefix`); returns the instructions that are left for the dense sweeps."""
+        pending = getattr(self, "_pending", None)
+        if pending is None or not instructions:
+            return instructions
+        consumed, state = prefix.sparse_prefix(instructions, pending, getattr(self, "prefix_support", None))
+        if consumed:
+            self._pending = state
+            self.stats["prefix_gates"] = self.stats.get("prefix_gates", 0) + consumed
+            self.stats["gate_ops"] += consumed
+        return instructions[consumed:]
 
     def _run_big(self, s):
         self._materialize()
         torch = _torch()
         k = len(s.positions)
         m = np.ascontiguousarray(s.matrix, dtype=self.np_dtype)
-        m_dev = torch.from_numpy(m.view(np.float32 if self.dtype == QB2_C64 else np.float64).reshape(-1)).to(self.device)
+        m_dev = self._upload_bytes(m.tobytes())
         tg = (ctypes.c_int * k)(*s.positions)
         dst = self._scratch_buf()
+        src = self._raw_state()
         _lib.check(
             self.lib.qb2_apply_matrix_big(
-                self.state.data_ptr(), dst.data_ptr(), self.n, self.hi_base, m_dev.data_ptr(), tg, k, s.cmask, s.cval,
+                src.data_ptr(), dst.data_ptr(), self.n, self.hi_base, m_dev.data_ptr(), tg, k, s.cmask, s.cval,
                 self.dtype, self._stream(),
             ),
             "qb2_apply_matrix_big",
         )
-        self.state, self._scratch = dst, self.state
+        self.state, self._scratch = dst, src
         self.stats["big"] += 1
 
 
@@ -103,7 +181,7 @@ class StateVector(DeviceOps):
     the reference's canonical order is ``pos[q] = num_qubits - 1 - q``.
     """
 
-    def __init__(self, num_qubits, dtype=np.complex64, device=None, T=None, r=None, L=4):
+    def __init__(self, num_qubits, dtype=np.complex64, device=None, T=None, r=None, L=4, tma=None, prefix_support=None):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.Qb2Error("the B200 engine needs a CUDA device; there is no CPU fallback")
@@ -120,7 +198,8 @@ class StateVector(DeviceOps):
         self.real = real
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         torch.cuda.set_device(self.device)
-        self.cfg = PlanConfig(self.n, self.dtype, T=T, r=r, L=L)
+        self.cfg = PlanConfig(self.n, self.dtype, T=T, r=r, L=L, tma=tma)
+        self.prefix_support = prefix_support  # None: the default of qrisp_b200.prefix; 0: no host prefix
         self.pos = [self.num_qubits - 1 - q for q in range(self.num_qubits)] + list(range(self.num_qubits, self.n))
         self.hi_base = 0
         self._buf = torch.empty(2 << self.n, dtype=real, device=self.device)
@@ -153,32 +232,45 @@ class StateVector(DeviceOps):
         return self._scratch
 
     def reset(self):
-        """Back to |0...0>.  Lazy: the first pass that runs synthesises the zeros instead of reading
-        them (one write and one read of the state saved); anything else that looks at the state
-        first makes :meth:`_materialize` write them."""
-        self._fresh = True
-
-    def _init_basis(self):
-        _lib.check(self.lib.qb2_init_basis(self._buf.data_ptr(), self.n, 0, self.dtype, self._stream()), "qb2_init_basis")
+        """Back to |0...0>.  Lazy: the state is PENDING -- a short list of non-zero amplitudes on the
+        host (:mod:`qrisp_b200.prefix`).  Gates are applied to the list while it stays short; the first
+        dense pass builds its tiles from it instead of reading 2**n zeros; anything else that looks at
+        the buffer first makes :meth:`_materialize` write it."""
+        self._pending = prefix.zero_state()
+        # no data sits in HBM any more, so the qubit map is free again: back to the canonical one (a
+        # reset engine is a new engine; compiled programs name the map they start from)
+        nq = self.num_qubits
+        self.pos[:] = [nq - 1 - q for q in range(nq)] + list(range(nq, self.n))
 
     def synchronize(self):
         _torch().cuda.current_stream(self.device).synchronize()
 
     # ------------------------------------------------------------------ gates
     def compile(self, instructions):
-        """Normalise + plan a list of unitary instructions against the CURRENT qubit map.
-        Returns a compiled program that :meth:`execute` runs; the map is advanced."""
+        """Normalise + plan a list of unitary instructions against the CURRENT qubit map (and, when the
+        state is still pending, the current sparse state: the program then starts with the host
+        prefix).  Returns a compiled program that :meth:`execute` runs; map and state move on as if the
+        program had run."""
+        pos_in = list(self.pos)
+        start = self._pending
+        instructions = self._take_prefix(list(instructions))
+        entry = self._pending
         # complex128 keeps non-unit diagonal entries exactly as given (see normalize.py)
         unit_tol = 1e-6 if self.dtype == QB2_C64 else 1e-13
         ops = normalize_circuit(instructions, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
-        return self.compile_ops(ops)
+        prog = self.compile_ops(ops, pos_in=pos_in, start=start, entry=entry)
+        return prog
 
-    def compile_ops(self, ops):
+    def compile_ops(self, ops, pos_in=None, start=None, entry=None):
+        pos_in = list(self.pos) if pos_in is None else pos_in
         planner = Planner(self.cfg, self.pos)
         steps, need = planner.plan(ops)
         if need is not None:
             raise _lib.Qb2Error(f"op needs non-local positions {need} on a single-device state")
-        return Program(self, steps)
+        prog = Program(self, steps, pos_in=pos_in, start=start, entry=entry)
+        self._pending = start  # nothing has run yet: the caller's state is what it was
+        self.pos[:] = pos_in
+        return prog
 
     def execute(self, program):
         program.run()
@@ -187,10 +279,13 @@ class StateVector(DeviceOps):
         """Plan and run in one go, STREAMING: every pass is launched the moment the planner has built
         it (launches are asynchronous), so the host plans pass k+1 while the device sweeps pass k and
         planning disappears from the wall time except for the first pass.  Returns the step list."""
+        self._guard()
+        instructions = self._take_prefix(list(instructions))
         unit_tol = 1e-6 if self.dtype == QB2_C64 else 1e-13
         ops = normalize_circuit(instructions, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
         planner = Planner(self.cfg, self.pos)
         keep = []  # device copies of the blobs stay alive until the launches have been issued
+        self._entry_pos = list(self.pos) if self._pending is not None else None
 
         def launch(step):
             if step.kind == "pass":
@@ -211,6 +306,7 @@ class StateVector(DeviceOps):
         if need is not None:
             raise _lib.Qb2Error(f"op needs non-local positions {need} on a single-device state")
         self._keep_alive = keep
+        self._entry_pos = None
         return steps
 
     def apply_matrix(self, matrix, qubits):
@@ -311,11 +407,20 @@ class StateVector(DeviceOps):
 
 
 class Program:
-    """A planned list of steps with its pass blobs resident on the device."""
+    """A planned list of steps with its pass blobs resident on the device.
 
-    def __init__(self, sv, steps):
+    A program is compiled against a qubit map (``pos_in``) and, when the state was still pending,
+    against that sparse state (``start``): :meth:`run` checks both, because the passes bake in physical
+    positions -- run against another map they would silently hit the wrong qubits.  ``entry`` is the
+    sparse state after the host prefix, which the first pass starts from; its device list is built once.
+    """
+
+    def __init__(self, sv, steps, pos_in=None, start=None, entry=None):
         self.sv = sv
         self.steps = steps
+        self.pos_in = list(sv.pos) if pos_in is None else list(pos_in)
+        self.pos_out = list(sv.pos)
+        self.start, self.entry = start, entry
         offs, total = [], 0
         for s in steps:
             if s.kind == "pass":
@@ -334,21 +439,41 @@ class Program:
                 self._headers.append(ctypes.create_string_buffer(s.blob[:small], small))
             else:
                 self._headers.append(None)
+        self._entry_sparse = None
+        if entry is not None and steps and steps[0].kind == "pass":
+            sv._entry_pos = self.pos_in  # the first pass sees the entry map (relabels come later)
+            self._entry_sparse = sv._sparse_for(steps[0], entry)
+            sv._entry_pos = None
         self.n_passes = sum(1 for s in steps if s.kind == "pass")
         self.n_kernel_ops = sum(s.n_ops for s in steps if s.kind == "pass")
         self.n_gate_ops = sum(s.n_gate_ops for s in steps if s.kind == "pass") + sum(1 for s in steps if s.kind == "big")
         self.n_phases = sum(s.n_phases for s in steps if s.kind == "pass")
 
+    def _enter(self):
+        sv = self.sv
+        sv._guard()
+        if list(sv.pos) != self.pos_in:
+            raise _lib.Qb2Error("this program was compiled against another qubit map (compile it where it runs, in order)")
+        if self.start is not None:
+            now = getattr(sv, "_pending", None)
+            if now is None or not (np.array_equal(now[0], self.start[0]) and np.array_equal(now[1], self.start[1])):
+                raise _lib.Qb2Error("this program was compiled for a state that has not been written yet (reset() first)")
+            sv._pending = self.entry
+        elif getattr(sv, "_pending", None) is not None:
+            sv._materialize()
+
     def run(self):
         sv = self.sv
+        self._enter()
+        first = True
         for s, o, h in zip(self.steps, self.offsets, self._headers):
             if s.kind == "pass":
-                sv._run_pass(s, h, self.dev, o)
+                sv._run_pass(s, h, self.dev, o, sparse=self._entry_sparse if first else None)
             else:
                 sv._run_big(s)
+            first = False
+        sv.pos[:] = self.pos_out  # (a state that is still pending is laid out by whatever map is current)
         sv.stats["passes"] += self.n_passes
         sv.stats["kernel_ops"] += self.n_kernel_ops
         sv.stats["gate_ops"] += self.n_gate_ops
         sv.stats["phases"] += self.n_phases
-
-

@@ -41,6 +41,10 @@ MAX_PHASES = 8
 MAX_SMALL_BYTES = 8192
 MAX_SLOTS = 32
 SMEM_PER_CTA = 113 * 1024  # two CTAs per SM
+# the TMA kernel (qb2_pass_tma.cuh): one CTA per SM, three 64 KB tile buffers; what is left of 227 KB
+TMA_AUX_BYTES = 232448 - 3 * 65536 - 1024
+MAX_SPARSE = 1024  # QB2_MAX_SPARSE: entries of a sparse input list
+FEATURE_FULL, FEATURE_TMA, FEATURE_ZERO_INPUT = 1, 2, 4
 MAX_TAB_BITS = 10
 MAX_PIECES = 6
 MAX_REG_TABS = 4
@@ -174,7 +178,7 @@ def fuse_butterfly_chains(recs, first, NR):
 class PlanConfig:
     """Tile geometry.  ``T`` tile bits, ``r`` register bits, ``L`` forced low positions."""
 
-    def __init__(self, n, dtype=QB2_C64, T=None, r=None, L=4):
+    def __init__(self, n, dtype=QB2_C64, T=None, r=None, L=4, tma=None):
         self.dtype = dtype
         # tuning knobs (bench sweeps): QB2_REG_BITS / QB2_TILE_BITS override the defaults
         if r is None and os.environ.get("QB2_REG_BITS"):
@@ -199,6 +203,9 @@ class PlanConfig:
         self.phase_slots = os.environ.get("QB2_NO_SLOTS") is None
         self.had_bfly = os.environ.get("QB2_NO_HAD") is None
         self.fuse_chains = os.environ.get("QB2_NO_CHAIN") is None
+        # passes whose tile is one box of a tensor map run on the TMA kernel (complex64, T=13, r=5)
+        want_tma = os.environ.get("QB2_NO_TMA") is None if tma is None else bool(tma)
+        self.tma = dtype == QB2_C64 and self.T == 13 and self.r == 5 and self.L == 4 and want_tma
 
     @property
     def TB(self):
@@ -221,9 +228,37 @@ class DescriptorOverflow(RuntimeError):
 class PassStep:
     kind = "pass"
 
-    def __init__(self, blob, n_ops, n_phases, tile_pos, n_gate_ops):
+    def __init__(self, blob, n_ops, n_phases, tile_pos, n_gate_ops, segs=(), R0=(), TP0=(), tma=False):
         self.blob, self.n_ops, self.n_phases, self.tile_pos = blob, n_ops, n_phases, tile_pos
         self.n_gate_ops = n_gate_ops
+        # what a sparse input list needs (engine.sparse_input_list): tile-number segments and the first
+        # phase's distribution (register positions, thread positions)
+        self.segs, self.R0, self.TP0 = list(segs), list(R0), list(TP0)
+        self.tma = tma
+
+
+def tma_tile_ok(tile_pos, n):
+    """Can the tile be ONE box of a rank-5 tensor map?  Positions 0..3 are dim 0 (a 128-byte line), one
+    dimension of box size 1 carries the non-tile bits, which leaves three dimensions for runs of higher tile
+    positions of at most 8 bits each (qb2_pass_tma.cuh make_tile_map)."""
+    if list(tile_pos[:4]) != [0, 1, 2, 3]:
+        return False
+    high = tile_pos[4:]
+    dims = 0
+    i = 0
+    while i < len(high):
+        j = i
+        while j + 1 < len(high) and high[j + 1] == high[j] + 1 and j + 1 - i < 8:
+            j += 1
+        dims += 1
+        i = j + 1
+    return dims <= 3
+
+
+def tma_columns(T):
+    """Slot (in amplitudes) of tile-index bit i in a tile buffer the TMA fills with the 128-byte swizzle:
+    row = index >> 4, the 16-byte chunk (index >> 1) & 7 is stored at chunk ^ (row & 7)."""
+    return [(1 << i) | ((1 << (i - 3)) if 4 <= i <= 6 else 0) for i in range(T)]
 
 
 # ----------------------------------------------------------------------------------------
@@ -399,6 +434,7 @@ class Planner:
             p += 1
         tile_pos = sorted(tile)
         assert len(tile_pos) == cfg.T and tile_pos[-1] < cfg.n
+        tma = cfg.tma and tma_tile_ok(tile_pos, cfg.n)
 
         # ---- phases: greedy, commutation aware
         phases = []  # (R list, ops)
@@ -457,10 +493,12 @@ class Planner:
         default_R = [x for x in reversed(tile_pos) if x not in low_lane][: cfg.r]
         if len(default_R) < cfg.r:
             default_R = list(reversed(tile_pos))[: cfg.r]
-        if set(phases[0][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
+        # (the TMA kernel moves tiles with bulk copies: any first / last distribution reads / writes the tile
+        # buffers directly, at worst with a two-way bank conflict)
+        if not tma and set(phases[0][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
             phases.insert(0, [list(default_R), [], False])
         sigma = {}
-        if set(phases[-1][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
+        if not tma and set(phases[-1][0]) & low_lane and len(default_R) == cfg.r and not (set(default_R) & low_lane):
             if cfg.store_relabel:
                 # The last phase holds some of the lowest positions in registers: a store under that
                 # distribution would scatter 8-byte words.  Instead of one more exchange the tile is
@@ -480,13 +518,13 @@ class Planner:
             raise DescriptorOverflow(f"{len(phases)} phases in one pass")
         scale0 = self.pending_scale
         try:
-            return self._pack(tile_pos, phases, sigma, settle), sigma
+            return self._pack(tile_pos, phases, sigma, settle, tma), sigma
         except DescriptorOverflow:
             self.pending_scale = scale0
             raise
 
     # -------------------------------------------------------------- packing
-    def _pack(self, tile_pos, phases, sigma=None, settle=True):
+    def _pack(self, tile_pos, phases, sigma=None, settle=True, tma=False):
         cfg = self.cfg
         T, r, TB, n = cfg.T, cfg.r, cfg.TB, cfg.n
         NR = 1 << r
@@ -506,6 +544,10 @@ class Planner:
         fixed += (csize << T) if len(phases) > 1 else 0
         fixed += 2 * MAX_SLOTS * fsize + 2 * MAX_SLOTS + 16
         slot_cap = max(0, min(MAX_SLOTS, (SMEM_PER_CTA - fixed) // (threads * fsize))) if cfg.phase_slots else 0
+        if tma:
+            # launch_kernel_tma's layout: roots, barriers, 8-byte thread contexts, slot area, sparse list
+            fixed = 2048 + 64 + len(phases) * threads * 8 + 4 * MAX_SLOTS * fsize + 2 * MAX_SLOTS + 16 + 4 * MAX_SPARSE + 16
+            slot_cap = max(0, min(MAX_SLOTS, (TMA_AUX_BYTES - fixed) // (threads * fsize))) if cfg.phase_slots else 0
 
         def add16(vals):
             off = len(a16)
@@ -525,6 +567,19 @@ class Planner:
             pcol = add64(1 << x for x in TP)
             rphys = add64(sum(((j >> i) & 1) << R[i] for i in range(r)) for j in range(NR))
             xw = xr = xflags = 0
+            if prev is None and tma:
+                # the tile buffers of the TMA kernel: this phase reads the buffer the load fills, the
+                # LAST phase writes the buffer the store drains
+                ccol = dict(zip(tile_pos, tma_columns(T)))
+                lR = phases[-1][0]
+                lTP = [x for x in tile_pos if x not in lR]
+                xw = add16([ccol[x] for x in lTP] + [_xor_cols(ccol, lR, j) for j in range(NR)])
+                xr = add16([ccol[x] for x in TP] + [_xor_cols(ccol, R, j) for j in range(NR)])
+                kw, kr = _regular_shift(ccol, lR, lTP), _regular_shift(ccol, R, TP)
+                if kw is not None:
+                    xflags |= 1 | (kw << 8)
+                if kr is not None:
+                    xflags |= 2 | (kr << 16)
             if prev is not None:
                 pR, pTP = prev
                 col = _slot_columns(tile_pos, pR, pTP, R, TP, cfg.conflict_bits)
@@ -692,8 +747,6 @@ class Planner:
             phases_b.append(struct.pack("<8I", first_op, op_count - first_op, pcol, rphys, xw, xr, xflags, 0))
             prev = (R, TP)
 
-        pf_feature, pf_index = 0, 0  # header.pf / QB2_FEATURE_PREFETCH: reserved (an L2 prefetch of the next tile did not pay)
-
         # ---- segments: tile id bits -> non-tile local positions
         segs = []
         src = 0
@@ -739,7 +792,7 @@ class Planner:
 
         # ops outside the lean kernel's repertoire (include/qrisp_b200.h QB2_FEATURE_FULL)
         features = 1 if any(rec[24] in (2, 3, 4, OP_DIAG) for rec in ops_b) else 0  # rec[24] = qb2_op.kind
-        features |= pf_feature
+        features |= FEATURE_TMA if tma else 0
         blob = bytearray(total)
         hdr = struct.pack(
             "<IIIIBBBBIIIIIIIIIIHH",
@@ -761,7 +814,7 @@ class Planner:
             tab_off,
             len(ops_b),
             features,
-            pf_index,
+            0,
             n_slots,
         )
         assert len(hdr) == 64
@@ -806,7 +859,9 @@ class Planner:
         if tables:
             tb = np.concatenate(tables)
             blob[tab_off : tab_off + tb.nbytes] = tb.tobytes()
-        return PassStep(bytes(blob), op_count, len(phases_b), tile_pos, n_gate_ops)
+        R0 = phases[0][0]
+        return PassStep(bytes(blob), op_count, len(phases_b), tile_pos, n_gate_ops, segs=segs, R0=R0,
+                        TP0=[x for x in tile_pos if x not in R0], tma=tma)
 
 
 class _RView:

@@ -53,15 +53,37 @@ def big_step_numpy(state, step):
     return out
 
 
-def emulate_statevector(qc, dtype=0, report=None, **plan_kw):
+def emulate_statevector(qc, dtype=0, report=None, sparse_start=False, max_support=None, **plan_kw):
+    """Plan ``qc`` and run the packed passes through the numpy emulator.  ``sparse_start``: as the engine
+    does it -- the host prefix (qb2_sparse_prefix) first, the first pass from the sparse input list."""
+    from qrisp_b200 import prefix
+
     instrs = [i for i in qc.data if i.matrix is not None]
     n = qc.num_qubits
+    cdt = np.complex64 if dtype == 0 else np.complex128
+    pending = None
+    if sparse_start:
+        consumed, pending = prefix.sparse_prefix(instrs, prefix.zero_state(), max_support)
+        instrs = instrs[consumed:]
     steps, pos, N = plan_circuit(instrs, n, dtype=dtype, **plan_kw)
-    st = np.zeros(1 << N, dtype=np.complex64 if dtype == 0 else np.complex128)
-    st[0] = 1
+    pos0 = [n - 1 - q for q in range(n)] + list(range(n, N))  # the map the first step sees
+    st = np.zeros(1 << N, dtype=cdt)
+    if pending is None:
+        st[0] = 1
+    elif not steps or steps[0].kind != "pass":
+        st[prefix.to_physical(pending[0], pos0, n).astype(np.int64)] = pending[1].astype(cdt)
+        pending = None
     for s in steps:
         if s.kind == "pass":
-            st = pass_emulator.run(s.blob, st, report=report)
+            sparse = None
+            if pending is not None:
+                phys = prefix.to_physical(pending[0], pos0, n)
+                data, k = prefix.sparse_input_list(s, phys, pending[1], N, 0, cdt)
+                pad = (4 * k + 15) // 16 * 16
+                sparse = (np.frombuffer(data, np.uint32, k, 0), np.frombuffer(data, np.uint32, k, pad), np.frombuffer(data, cdt, k, 2 * pad))
+                st = np.full(1 << N, np.nan, dtype=cdt)  # never read
+                pending = None
+            st = pass_emulator.run(s.blob, st, report=report, sparse=sparse)
         else:
             st = big_step_numpy(st, s)
     return canonical(st, pos, n), steps

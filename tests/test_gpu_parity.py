@@ -95,7 +95,7 @@ def test_gpu_matches_emulator_bitwise_layout():
     qc = random_circuit(14, 6, seed=77, two_qubit="cx")
     qc.cp(0.3, 0, 13)
     qc.mcx([0, 13], 5)
-    sv = StateVector(14)
+    sv = StateVector(14, prefix_support=0)  # no host prefix: the same gate list goes to both planners
     instrs = [i for i in qc.data if i.matrix is not None]
     steps, pos, N = plan_circuit(instrs, 14)
     prog = sv.compile(instrs)

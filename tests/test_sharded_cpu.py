@@ -38,16 +38,32 @@ def _worker(rank, world, port, case, out_dir):
         from qrisp_b200.distributed import ShardedStateVector, _canonical
 
         class CpuShard(ShardedStateVector):
+            prefix_support = 2  # a short host prefix (a GHZ ladder fits): the default (1024) would finish these circuits before any swap
+
             def _setup_device(self, device):
                 self.device = torch.device("cpu")
                 self.state = torch.zeros(2 << self.n, dtype=torch.float32)
                 self._scratch = torch.zeros_like(self.state)
 
-            def reset(self):
-                self._fresh_layout = True  # as the real reset: the planner may choose who starts on the rank bits
-                self.state.zero_()
-                if self.rank == 0:
-                    self.state[0] = 1.0
+            # reset() is the product's: the state is a pending sparse list until the first pass runs
+
+            def _sparse_for(self, step, state):
+                from qrisp_b200 import prefix
+
+                phys = prefix.to_physical(state[0], self.pos, len(self.pos))
+                data, k = prefix.sparse_input_list(step, phys, state[1], self.n, self.hi_base, np.complex64)
+                pad = (4 * k + 15) // 16 * 16
+                return (np.frombuffer(data, np.uint32, k, 0), np.frombuffer(data, np.uint32, k, pad),
+                        np.frombuffer(data, np.complex64, k, 2 * pad)), k
+
+            def _init_sparse(self, state):
+                from qrisp_b200 import prefix
+
+                phys = prefix.to_physical(state[0], self.pos, len(self.pos))
+                mine = (phys >> np.uint64(self.n)) == np.uint64(self.rank)
+                st = np.zeros(1 << self.n, dtype=np.complex64)
+                st[(phys[mine] & np.uint64((1 << self.n) - 1)).astype(np.int64)] = state[1][mine].astype(np.complex64)
+                self.state = torch.from_numpy(st.view(np.float32).copy())
 
             def _np(self):
                 return self.state.numpy().view(np.complex64)
@@ -65,12 +81,17 @@ def _worker(rank, world, port, case, out_dir):
             def _upload_blobs(self, steps, offs, total):
                 return None
 
-            def _run_pass(self, step, header, dev, offset):
-                out = pass_emulator.run(step.blob, self._np(), hi_base=self.hi_base)
+            def _run_pass(self, step, header, dev, offset, sparse=None):
+                lst = None
+                if self._pending is not None:
+                    lst = (sparse if sparse is not None else self._sparse_for(step, self._pending))[0]
+                    self._pending = None
+                out = pass_emulator.run(step.blob, self._np(), hi_base=self.hi_base, sparse=lst)
                 self.state = torch.from_numpy(out.view(np.float32).copy())
 
             def _run_big(self, s):
                 # rank bits enter the control mask through the physical index
+                self._materialize()
                 st = self._np()
                 idx = np.arange(st.size) | self.hi_base
                 full_on = ((idx ^ s.cval) & s.cmask) == 0

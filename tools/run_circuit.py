@@ -15,7 +15,6 @@ sv = StateVector(n)
 t0 = time.perf_counter()
 prog = sv.compile(instrs)
 t_plan = time.perf_counter() - t0
-pos_after = list(sv.pos)
 best = None
 for rep in range(int(os.environ.get("RUN_REPS", 3))):  # the first run also pays for the first touch of the buffers
     sv.reset()
@@ -25,7 +24,6 @@ for rep in range(int(os.environ.get("RUN_REPS", 3))):  # the first run also pays
     ms_ = e0.elapsed_time(e1)
     best = ms_ if best is None else min(best, ms_)
 ms = best
-sv.pos[:] = pos_after
 norm = sv.norm2()
 state_bytes = 8 << n
 print(json.dumps({"circuit": kind, "qubits": n, "gates": len(instrs), "plan_s": round(t_plan, 3), "sweep_ms": round(ms, 2),
