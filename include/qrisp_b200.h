@@ -145,6 +145,16 @@ int qb2_norm2(const void *state, int n, double *out_dev, int dtype, void *stream
 int qb2_probabilities(const void *state, int n, uint64_t hi_base, const int *mes_pos, int m, double *probs_dev,
                       int dtype, void *stream);
 
+/* Outcome pruning on the device: for more than 10 measured qubits the reference keeps the outcomes with
+ * p > max(p) * cutoff_ratio (bi_arrays.py:1030-1055 -> bi_array_helper.py:315-331), so only those need to
+ * reach the host.  Two calls over the 2**m doubles of qb2_probabilities:
+ *   capacity == 0: scratch_dev[0] = bit pattern of max(p), scratch_dev[1] = number of survivors;
+ *   capacity  > 0: idx_dev / val_dev [capacity] receive the survivors (any order; scratch_dev[1] counts again;
+ *                  scratch_dev[0] must still hold the maximum of the first call).
+ * scratch_dev: two uint64 on the device. */
+int qb2_prune_probabilities(const double *probs_dev, int m, double cutoff_ratio, uint64_t *scratch_dev, uint64_t *idx_dev,
+                            double *val_dev, uint64_t capacity, void *stream);
+
 /* Shot sampling: replaces numpy.random.choice over cl_prob (simulator.py:190-201) without
  * materialising the 2**m probability vector.
  *   qb2_sample_prepare: chunk_sums_dev[c] = sum of |amp|^2 over chunk c (2**chunk_bits

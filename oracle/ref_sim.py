@@ -228,6 +228,25 @@ def rewrite_measurements(circuit):
             out.append(Instruction("cx", (fresh, q), (), CX))
         elif instr.name in ("qb_dealloc", "disentangle"):
             continue
+        elif getattr(instr, "ctrl_state", None) is not None:
+            # reference: circuit_preprocessing.py:790-816 (ClControlledOperation): controls on the qubits
+            # that carry the outcomes; an unwritten clbit with ctrl_state "0" gets a fresh |0> qubit, with
+            # "1" the operation is dropped
+            ctrl_qubits = []
+            for cb, want in zip(instr.clbits, instr.ctrl_state):
+                if cb not in cb_to_qb:
+                    if want == "1":
+                        break
+                    ctrl_qubits.append(n)
+                    n += 1
+                else:
+                    ctrl_qubits.append(cb_to_qb[cb])
+            else:
+                k, nb = len(ctrl_qubits), instr.matrix.shape[0]
+                m = np.eye(nb << k, dtype=np.complex128)
+                cs = int(instr.ctrl_state, 2) if k else 0
+                m[cs * nb : (cs + 1) * nb, cs * nb : (cs + 1) * nb] = instr.matrix  # unitary_management.py:68-88
+                out.append(Instruction(instr.name, tuple(ctrl_qubits) + tuple(instr.qubits), (), m))
         else:
             out.append(instr)
     for c, q in cb_to_qb.items():

@@ -52,6 +52,10 @@ SYMBOLS = {
         _c.c_int,
         [_c.c_void_p, _c.c_int, _c.c_uint64, _c.POINTER(_c.c_int), _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p],
     ),
+    "qb2_prune_probabilities": (
+        _c.c_int,
+        [_c.c_void_p, _c.c_int, _c.c_double, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_void_p],
+    ),
     "qb2_sample_chunk_bits": (_c.c_int, [_c.c_int]),
     "qb2_sample_prepare": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "qb2_sample_draw": (

@@ -39,9 +39,9 @@ class Instruction:
     """One circuit instruction: a name, integer qubit/clbit indices and (for unitary
     instructions) the ``2**k x 2**k`` matrix in the reference's big-endian convention."""
 
-    __slots__ = ("name", "qubits", "clbits", "matrix", "params", "warning")
+    __slots__ = ("name", "qubits", "clbits", "matrix", "params", "warning", "ctrl_state")
 
-    def __init__(self, name, qubits, clbits=(), matrix=None, params=(), warning=False):
+    def __init__(self, name, qubits, clbits=(), matrix=None, params=(), warning=False, ctrl_state=None):
         self.name = str(name)
         self.qubits = tuple(int(q) for q in qubits)
         self.clbits = tuple(int(c) for c in clbits)
@@ -55,6 +55,11 @@ class Instruction:
         self.matrix = matrix
         self.params = tuple(params)
         self.warning = bool(warning)
+        # classically controlled operation (reference: circuit/operation.py ClControlledOperation): ``matrix``
+        # is the BASE operation on ``qubits``; it is applied when clbit ``clbits[j]`` holds ``ctrl_state[j]``
+        self.ctrl_state = None if ctrl_state is None else str(ctrl_state)
+        if self.ctrl_state is not None and len(self.ctrl_state) != len(self.clbits):
+            raise ValueError("ctrl_state needs one character per control clbit")
 
     @property
     def num_qubits(self):
@@ -64,7 +69,7 @@ class Instruction:
         return self.matrix is not None
 
     def copy(self):
-        return Instruction(self.name, self.qubits, self.clbits, self.matrix, self.params, self.warning)
+        return Instruction(self.name, self.qubits, self.clbits, self.matrix, self.params, self.warning, self.ctrl_state)
 
     def __repr__(self):
         return f"Instruction({self.name!r}, qubits={self.qubits}, clbits={self.clbits})"
@@ -156,12 +161,12 @@ class Circuit:
         self.num_clbits += 1
         return self.num_clbits - 1
 
-    def append(self, name, qubits, clbits=(), matrix=None, params=(), warning=False):
+    def append(self, name, qubits, clbits=(), matrix=None, params=(), warning=False, ctrl_state=None):
         if isinstance(qubits, (int, np.integer)):
             qubits = (qubits,)
         if isinstance(clbits, (int, np.integer)):
             clbits = (clbits,)
-        instr = Instruction(name, qubits, clbits, matrix, params, warning)
+        instr = Instruction(name, qubits, clbits, matrix, params, warning, ctrl_state)
         for q in instr.qubits:
             if not 0 <= q < self.num_qubits:
                 raise IndexError(f"qubit index {q} out of range for {self.num_qubits} qubits")
@@ -280,6 +285,17 @@ class Circuit:
         controls = list(controls)
         return self.append("mcp", controls + [target], matrix=_controlled(p_matrix(phi), len(controls)), params=(phi,))
 
+    def c_if(self, matrix, qubits, clbits, ctrl_state=None, name="c_if_unitary"):
+        """``matrix`` on ``qubits`` if the classical bits ``clbits`` hold ``ctrl_state`` (a string, one
+        character per clbit, default all ones) -- the reference's ``Operation.c_if``
+        (circuit/operation.py:869-915)."""
+        if isinstance(clbits, (int, np.integer)):
+            clbits = (clbits,)
+        clbits = tuple(clbits)
+        if ctrl_state is None:
+            ctrl_state = "1" * len(clbits)
+        return self.append(name, qubits, clbits, matrix=matrix, ctrl_state=ctrl_state)
+
     def measure(self, qubits, clbits=None):
         if isinstance(qubits, (int, np.integer)):
             qubits = [qubits]
@@ -322,9 +338,12 @@ class Circuit:
                 res.append(name, qubits, clbits, warning=getattr(op, "warning", False))
                 continue
             if clbits:
-                raise NotImplementedError(
-                    f"classically controlled operation {name!r} is not supported by the B200 path"
-                )
+                # classically controlled (reference: circuit_preprocessing.py:790-816 reads base_op and ctrl_state)
+                base, cs = getattr(op, "base_op", None), getattr(op, "ctrl_state", None)
+                if base is None or cs is None:
+                    raise NotImplementedError(f"operation {name!r} with classical bits is neither measure nor c_if")
+                res.append(name, qubits, clbits, matrix=np.asarray(base.get_unitary()), ctrl_state=str(cs))
+                continue
             matrix = np.asarray(op.get_unitary())
             if matrix.dtype == np.dtype("O"):
                 raise TypeError(f"operation {name!r} has unbound abstract parameters")
@@ -334,9 +353,10 @@ class Circuit:
 
     def to_arrays(self):
         """Flatten into numpy arrays (used for the golden fixtures under tests/golden)."""
-        names, qoff, qidx, coff, cidx, moff, mdat, warn = [], [0], [], [0], [], [0], [], []
+        names, qoff, qidx, coff, cidx, moff, mdat, warn, cstate = [], [0], [], [0], [], [0], [], [], []
         for i in self.data:
             names.append(i.name)
+            cstate.append("" if i.ctrl_state is None else "c" + i.ctrl_state)
             qidx.extend(i.qubits)
             qoff.append(len(qidx))
             cidx.extend(i.clbits)
@@ -356,6 +376,7 @@ class Circuit:
             "moff": np.array(moff, dtype=np.int64),
             "mdat": np.concatenate(mdat) if mdat else np.zeros(0, dtype=np.complex128),
             "warn": np.array(warn, dtype=bool),
+            "cstate": np.array(cstate, dtype="U16"),
         }
 
     @classmethod
@@ -366,6 +387,7 @@ class Circuit:
             g("names"), g("qoff"), g("qidx"), g("coff"), g("cidx"), g("moff"), g("mdat"),
         )
         warn = g("warn")
+        cstate = arrs[prefix + "cstate"] if (prefix + "cstate") in arrs else None
         for j in range(len(names)):
             qubits = qidx[qoff[j] : qoff[j + 1]]
             clbits = cidx[coff[j] : coff[j + 1]]
@@ -373,7 +395,8 @@ class Circuit:
             if moff[j + 1] > moff[j]:
                 dim = 1 << len(qubits)
                 matrix = mdat[moff[j] : moff[j + 1]].reshape(dim, dim)
-            res.data.append(Instruction(str(names[j]), qubits, clbits, matrix, (), bool(warn[j])))
+            cs = None if cstate is None or not str(cstate[j]) else str(cstate[j])[1:]
+            res.data.append(Instruction(str(names[j]), qubits, clbits, matrix, (), bool(warn[j]), cs))
         return res
 
 

@@ -137,6 +137,12 @@ int qb2_probabilities(const void *state, int n, uint64_t hi_base, const int *mes
     return launch_probabilities(state, n, hi_base, mes_pos, m, probs_dev, dtype, (cudaStream_t)stream);
 }
 
+int qb2_prune_probabilities(const double *probs_dev, int m, double cutoff_ratio, uint64_t *scratch_dev, uint64_t *idx_dev,
+                            double *val_dev, uint64_t capacity, void *stream) {
+    return launch_prune(probs_dev, m, cutoff_ratio, reinterpret_cast<unsigned long long *>(scratch_dev), idx_dev, val_dev, capacity,
+                        (cudaStream_t)stream);
+}
+
 int qb2_sample_chunk_bits(int n) { return sample_chunk_bits(n); }
 
 int qb2_sample_prepare(const void *state, int n, double *chunk_sums_dev, int dtype, void *stream) {

@@ -84,5 +84,7 @@ int launch_sample_prepare(const void *state, int n, double *chunk_sums_dev, int 
 int launch_sample_draw(const void *state, int n, const double *chunk_sums_dev, const double *uniforms_dev,
                        int64_t shots, uint64_t *indices_dev, int dtype, cudaStream_t s);
 int sample_chunk_bits(int n);
+int launch_prune(const double *probs_dev, int m, double ratio, unsigned long long *scratch_dev, uint64_t *idx_dev, double *val_dev,
+                 uint64_t capacity, cudaStream_t s);
 
 }  // namespace qb2

@@ -440,6 +440,62 @@ int launch_sample_draw(const void *state, int n, const double *chunk_sums_dev, c
     return check_cuda(cudaGetLastError(), "sample_draw launch");
 }
 
+// ---- outcome pruning on the device: the reference keeps, for more than 10 measured qubits, the outcomes
+// with p > max(p) * cutoff_ratio (bi_array_helper.py:315-331) -- a max and a compare.  Three small kernels
+// over the 2**m probabilities: max, count, compact.  Only the survivors travel to the host.
+namespace {
+__global__ void prob_max_kernel(const double *__restrict__ p, const uint64_t size, unsigned long long *__restrict__ out) {
+    __shared__ double sh[32];
+    double m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (uint64_t)gridDim.x * blockDim.x)
+        m = fmax(m, p[i]);
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+        for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        // non-negative doubles order like their bit patterns
+        if (threadIdx.x == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+    }
+}
+__global__ void prob_compact_kernel(const double *__restrict__ p, const uint64_t size, const unsigned long long *__restrict__ maxbits,
+                                    const double ratio, unsigned long long *__restrict__ count, uint64_t *__restrict__ idx,
+                                    double *__restrict__ val, const uint64_t capacity) {
+    const double thr = __longlong_as_double((long long)*maxbits) * ratio;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double v = p[i];
+        if (v > thr) {
+            const unsigned long long at = atomicAdd(count, 1ull);
+            if (at < capacity) {  // (capacity 0: the counting run)
+                idx[at] = i;
+                val[at] = v;
+            }
+        }
+    }
+}
+}  // namespace
+
+int launch_prune(const double *probs_dev, int m, double ratio, unsigned long long *scratch_dev, uint64_t *idx_dev, double *val_dev,
+                 uint64_t capacity, cudaStream_t s) {
+    if (!probs_dev || !scratch_dev || m < 0 || m > 34) return set_error(QB2_EINVAL, "qb2_prune_probabilities: bad arguments");
+    if (capacity && (!idx_dev || !val_dev)) return set_error(QB2_EINVAL, "qb2_prune_probabilities: null output");
+    const uint64_t size = 1ull << m;
+    uint64_t blocks = (size + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (capacity == 0) {  // first call: maximum and survivor count (scratch[0] = max bits, scratch[1] = count)
+        QB2_CUDA(cudaMemsetAsync(scratch_dev, 0, 16, s));
+        prob_max_kernel<<<(unsigned)blocks, 256, 0, s>>>(probs_dev, size, scratch_dev);
+        count_launch();
+    } else {  // second call: compact (the maximum is still in scratch[0])
+        QB2_CUDA(cudaMemsetAsync(scratch_dev + 1, 0, 8, s));
+    }
+    prob_compact_kernel<<<(unsigned)blocks, 256, 0, s>>>(probs_dev, size, scratch_dev, ratio, scratch_dev + 1, idx_dev, val_dev, capacity);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "prune launch");
+}
+
 int launch_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev, const int *targets,
                       int k, uint64_t cmask, uint64_t cval, int dtype, cudaStream_t s) {
     if (!src || !dst || src == dst || !matrix_dev || !targets || n < 1 || n > 40)

@@ -247,6 +247,25 @@ class ShardedStateVector(DeviceOps):
         self.io["d2h"] += probs.numel() * 8
         return probs.cpu().numpy()
 
+    def amplitudes(self, indices):
+        """Amplitudes at the given basis states (reference order: qubit 0 = most significant bit), on every
+        rank: each rank gathers the ones it holds, a sum over ranks completes the list."""
+        self._materialize()
+        import torch
+
+        idx = np.asarray(indices, dtype=np.uint64)
+        nq = self.num_qubits
+        phys = np.zeros(idx.shape, dtype=np.uint64)
+        for q in range(nq):
+            phys |= ((idx >> np.uint64(nq - 1 - q)) & np.uint64(1)) << np.uint64(self.pos[q])
+        mine = (phys >> np.uint64(self.n)) == np.uint64(self.rank)
+        local = torch.from_numpy((phys & np.uint64((1 << self.n) - 1)).astype(np.int64)).to(self.device)
+        vals = self.state.view(-1, 2)[local].to(torch.float64)
+        vals = vals * torch.from_numpy(mine.astype(np.float64)).to(self.device)[:, None]
+        self.dist.all_reduce(vals, group=self.group)
+        v = vals.cpu().numpy()
+        return (v[:, 0] + 1j * v[:, 1]).astype(self.np_dtype)
+
     def norm2(self):
         self._materialize()
         import torch

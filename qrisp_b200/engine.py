@@ -338,6 +338,22 @@ class StateVector(DeviceOps):
         self.io["d2h"] += host.nbytes
         return host.view(self.np_dtype).copy()
 
+    def amplitudes(self, indices):
+        """Amplitudes at the given basis states (integers in the reference's order: qubit 0 = most
+        significant bit) -- a gather of a few entries, for spot checks of states too large to copy out."""
+        self._materialize()
+        torch = _torch()
+        idx = np.asarray(indices, dtype=np.uint64)
+        nq = self.num_qubits
+        phys = np.zeros(idx.shape, dtype=np.uint64)
+        for q in range(nq):
+            phys |= ((idx >> np.uint64(nq - 1 - q)) & np.uint64(1)) << np.uint64(self.pos[q])
+        sel = torch.from_numpy(phys.astype(np.int64)).to(self.device)
+        vals = self.state.view(-1, 2)[sel].cpu().numpy()
+        self.io["h2d"] += phys.nbytes
+        self.io["d2h"] += vals.nbytes
+        return (vals[:, 0] + 1j * vals[:, 1]).astype(self.np_dtype)
+
     def norm2(self):
         self._materialize()
         torch = _torch()

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .circuit import NON_UNITARY, STRUCTURAL, Instruction
+from .circuit import NON_UNITARY, STRUCTURAL, Instruction, _controlled
 
 _CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
 
@@ -95,6 +95,24 @@ def unitarize(circuit):
             n += 1
             unitary.append(Instruction("cx", (q, fresh), (), _CX))
             unitary.append(Instruction("cx", (fresh, q), (), _CX))
+        elif instr.ctrl_state is not None:
+            # classically controlled operation (reference: circuit_preprocessing.py:790-816): a control on
+            # the qubit that carries the clbit's outcome.  A clbit nobody has written yet reads 0: the
+            # operation never fires if it wants a 1, and a fresh |0> qubit stands in if it wants a 0.
+            controls = []
+            fires = True
+            for c, want in zip(instr.clbits, instr.ctrl_state):
+                if c in outcome_qubit:
+                    controls.append(outcome_qubit[c])
+                elif want == "1":
+                    fires = False
+                    break
+                else:
+                    controls.append(n)
+                    n += 1
+            if fires:
+                m = _controlled(instr.matrix, len(controls), int(instr.ctrl_state, 2)) if controls else instr.matrix
+                unitary.append(Instruction(instr.name, tuple(controls) + instr.qubits, (), m))
         elif instr.matrix is None:
             raise NotImplementedError(f"instruction {instr.name!r} has no unitary and is not measure/reset")
         else:

@@ -64,13 +64,50 @@ def round_probabilities(cl_prob):
     return cl_prob / np.sum(cl_prob)
 
 
-def run(qc, shots=None, token="", dtype=np.complex64, seed=None, return_engine=False, **engine_kwargs):
-    """Simulate ``qc`` and return its measurement statistics.
+def _device_outcomes(sv, mes_qubits):
+    """Outcomes the reference keeps for more than 10 measured qubits, pruned ON THE DEVICE: the dense
+    distribution (2**m doubles) stays in HBM, only ``p > max(p) * cutoff_ratio`` travels
+    (reference: bi_arrays.py:1030-1055 -> bi_array_helper.py:315-331)."""
+    import ctypes
 
-    ``shots=None``: dict ``bitstring -> probability``; ``shots=k``: dict ``bitstring ->
-    count``.  ``token`` is accepted for signature compatibility and ignored, as in the
-    reference.  ``seed`` fixes the sampled counts.
+    import torch
+
+    from . import _lib
+
+    m = len(mes_qubits)
+    probs = sv.probabilities(mes_qubits, to_host=False)
+    scratch = torch.zeros(2, dtype=torch.int64, device=sv.device)
+    ratio = float(CUTOFF_RATIO)
+    stream = sv._stream()
+    _lib.check(sv.lib.qb2_prune_probabilities(probs.data_ptr(), m, ratio, scratch.data_ptr(), None, None, 0, stream), "qb2_prune_probabilities")
+    count = int(scratch[1].item())
+    idx = torch.empty(count, dtype=torch.int64, device=sv.device)
+    val = torch.empty(count, dtype=torch.float64, device=sv.device)
+    _lib.check(
+        sv.lib.qb2_prune_probabilities(probs.data_ptr(), m, ratio, scratch.data_ptr(), idx.data_ptr(), val.data_ptr(), count, stream),
+        "qb2_prune_probabilities",
+    )
+    keep, p = idx.cpu().numpy(), val.cpu().numpy()
+    sv.io["d2h"] += 16 * count + 16
+    order = np.argsort(keep, kind="stable")  # the compaction's order is not deterministic; the reference's is ascending
+    keep, p = keep[order], p[order]
+    return keep.astype(np.int64), p / p.sum()
+
+
+def run(qc, shots=None, token="", iqs=None, insert_reset=True, dtype=np.complex64, seed=None, return_engine=False,
+        group=None, **engine_kwargs):
+    """Simulate ``qc`` and return its measurement statistics -- the drop-in for
+    ``qrisp.simulator.run(qc, shots, token="", iqs=None, insert_reset=True)`` (reference: simulator.py:44).
+
+    ``shots=None``: dict ``bitstring -> probability``; ``shots=k``: dict ``bitstring -> count``.  ``token`` is
+    accepted and ignored, as in the reference.  ``insert_reset`` only makes the reference sprinkle
+    ``disentangle`` hints for its factored state (circuit_preprocessing.py:466-491): no effect on a dense
+    state.  ``iqs`` (a reference ``QuantumState`` to start from) has no B200 counterpart.  ``seed`` fixes the
+    sampled counts.  ``group``: a ``torch.distributed`` process group -- every rank calls ``run`` with the same
+    arguments, the state is sharded over the ranks' GPUs and every rank gets the result.
     """
+    if iqs is not None:
+        raise NotImplementedError("run(iqs=...): starting from a reference QuantumState object is not supported on the B200 path")
     qc = _as_circuit(qc)
     if len(qc.data) == 0:
         return {"": shots}
@@ -79,7 +116,12 @@ def run(qc, shots=None, token="", dtype=np.complex64, seed=None, return_engine=F
     if count_measurements(qc.data) == 0:
         return {"": 1.0}
     instrs, n, measurements = unitarize(qc)
-    sv = StateVector(n, dtype=dtype, **engine_kwargs)
+    if group is None:
+        sv = StateVector(n, dtype=dtype, **engine_kwargs)
+    else:
+        from .distributed import ShardedStateVector
+
+        sv = ShardedStateVector(n, group=group, dtype=dtype, **engine_kwargs)
     sv.apply_circuit(instrs)
     # reference: simulator.py:151-157 -- outcome bit order = descending clbit index
     measurements.sort(key=lambda x: -x[1])
@@ -87,8 +129,10 @@ def run(qc, shots=None, token="", dtype=np.complex64, seed=None, return_engine=F
     width = len(mes_qubits)
     res = {}
     if width <= MAX_DENSE_OUTCOME_BITS:
-        p = sv.probabilities(mes_qubits)
-        outcomes, probs = prune_outcomes(p)
+        if width > 10 and group is None:
+            outcomes, probs = _device_outcomes(sv, mes_qubits)
+        else:
+            outcomes, probs = prune_outcomes(sv.probabilities(mes_qubits))
         probs = round_probabilities(probs)
         if shots is None:
             for o, pr in zip(outcomes, probs):
@@ -99,19 +143,15 @@ def run(qc, shots=None, token="", dtype=np.complex64, seed=None, return_engine=F
         else:
             rng = np.random.default_rng(seed)
             samples = rng.choice(len(probs), int(shots), p=probs)
-            hist = np.bincount(samples, minlength=len(probs))
-            for i in np.flatnonzero(hist):
-                res[bin(int(outcomes[i]))[2:].zfill(width)] = int(hist[i])
+            res = counts_dict(outcomes[samples].astype(np.uint64), width)
     else:
         if shots is None:
             raise MemoryError(
                 f"{width} measured qubits: the full distribution has 2**{width} entries; pass shots=... to sample it"
             )
-        rng = np.random.default_rng(seed)
-        outs = sv.sample(int(shots), mes_qubits, rng=rng)
-        vals, counts = np.unique(outs, return_counts=True)
-        for v, c in zip(vals, counts):
-            res[bin(int(v))[2:].zfill(width)] = int(c)
+        # wide registers: shots are drawn on the device straight from the amplitudes
+        outs = sv.sample(int(shots), mes_qubits, rng=np.random.default_rng(seed))
+        res = counts_dict(outs, width)
     _record_io(sv)
     if return_engine:
         return res, sv
@@ -163,14 +203,4 @@ def statevector_sim(qc, dtype=np.complex64, **engine_kwargs):
     return res
 
 
-class B200Backend:
-    """Counterpart of the reference's default backend object (reference:
-    interface/simulators/qrisp_simulator_backend.py ``def_backend``): ``backend.run(qc,
-    shots)`` returns the counts dict."""
-
-    def __init__(self, dtype=np.complex64, **engine_kwargs):
-        self.dtype = dtype
-        self.engine_kwargs = engine_kwargs
-
-    def run(self, qc, shots=None, token=""):
-        return run(qc, shots, token, dtype=self.dtype, **self.engine_kwargs)
+from .backend import B200Backend, B200Job, B200JobResult, make_qrisp_backend  # noqa: E402,F401  (the default-backend drop-in)

@@ -19,6 +19,9 @@ Fixtures written (all small .npz files):
 * programs.npz     -- circuits Qrisp itself compiled (BASELINE.json configs[0]: QuantumFloat
                       h + inverse QFT; configs[2]: Shor ``find_order``) + what ``run`` returned
 * fusion.npz       -- ``group_qc`` output: every grouped instruction's qubits and unitary
+* cif.npz          -- circuits with classically controlled operations (``op.c_if``) + ``run(qc, None)``
+* shor.npz         -- BASELINE.json configs[2] at the named sizes: ``find_order`` circuits for N=35 and
+                      N=77 as Qrisp compiled them + what ``run`` returned + the reference's wall time
 """
 
 import math
@@ -341,9 +344,116 @@ def make_fusion():
     print("fusion.npz:", names)
 
 
+def make_cif():
+    """Classically controlled operations (reference: circuit_preprocessing.py:790-816)."""
+    from qrisp import XGate, RYGate, HGate
+
+    out = {}
+    cases = []
+    # teleportation-style correction: the outcome of qubit 0 decides an X on qubit 1
+    qc = QuantumCircuit(2, 1)
+    qc.h(0)
+    qc.measure(qc.qubits[0], qc.clbits[0])
+    qc.append(XGate().c_if(1), [qc.qubits[1]], [qc.clbits[0]])
+    qc.ry(0.4, 1)
+    qc.measure(qc.qubits[1])
+    cases.append(("cif_x", qc))
+    # two control bits with a mixed control state, a rotation as the base operation
+    qc = QuantumCircuit(4, 2)
+    qc.ry(1.1, 0)
+    qc.ry(0.6, 1)
+    qc.cx(0, 2)
+    qc.measure(qc.qubits[0], qc.clbits[0])
+    qc.measure(qc.qubits[1], qc.clbits[1])
+    qc.append(RYGate(0.9).c_if(2, "10"), [qc.qubits[3]], [qc.clbits[0], qc.clbits[1]])
+    qc.append(HGate().c_if(2, "01"), [qc.qubits[2]], [qc.clbits[0], qc.clbits[1]])
+    qc.h(0)
+    qc.measure(qc.qubits[2])
+    qc.measure(qc.qubits[3])
+    qc.measure(qc.qubits[0])
+    cases.append(("cif_mixed", qc))
+    # a control bit nobody has written: "0" fires always, "1" never
+    qc = QuantumCircuit(2, 2)
+    qc.append(XGate().c_if(1, "0"), [qc.qubits[0]], [qc.clbits[0]])
+    qc.append(XGate().c_if(1, "1"), [qc.qubits[1]], [qc.clbits[1]])
+    qc.ry(0.3, 1)
+    qc.measure(qc.qubits[0])
+    qc.measure(qc.qubits[1])
+    cases.append(("cif_unwritten", qc))
+    names = []
+    for name, qc in cases:
+        res = quiet(run, qc.copy(), None)
+        pack(name + "_", Circuit.from_qrisp(qc), out)
+        keys = sorted(res.keys())
+        out[name + "_keys"] = np.array(keys)
+        out[name + "_probs"] = np.array([res[k] for k in keys], dtype=np.float64)
+        names.append(name)
+        print(name, res)
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "cif.npz"), **out)
+    print("cif.npz:", names)
+
+
+def make_shor():
+    """BASELINE.json configs[2] at the sizes it names (README ``find_order``, N = 35 and N = 77), captured at
+    the backend boundary like make_programs; the reference's own wall time goes along (its sparse,
+    entanglement-factored state makes these cheap on a CPU)."""
+    import time
+
+    import qrisp.interface.simulators.qrisp_simulator_backend as be
+    from qrisp import QuantumModulus, control
+
+    captured = []
+    orig = be.default_run
+
+    def spy(qc, shots, token=""):
+        t0 = time.perf_counter()
+        res = orig(qc.copy(), shots, token)
+        captured.append((qc.copy(), shots, res, time.perf_counter() - t0))
+        return res
+
+    be.default_run = spy
+    out, names = {}, []
+
+    def find_order_mes(a_, N):
+        qg = QuantumModulus(N)
+        qg[:] = 1
+        qpe_res = QuantumFloat(2 * qg.size + 1, exponent=-(2 * qg.size + 1))
+        h(qpe_res)
+        x = a_
+        for i in range(len(qpe_res)):
+            with control(qpe_res[i]):
+                qg *= x
+                x = (x * x) % N
+        QFT(qpe_res, inv=True)
+        return dict(qpe_res.get_measurement())
+
+    for a_, N in ((4, 35), (2, 77)):
+        quiet(find_order_mes, a_, N)
+        qc, shots, res, secs = captured[-1]
+        name = f"shor_order_a{a_}_N{N}"
+        pack(name + "_", Circuit.from_qrisp(qc), out)
+        keys = sorted(res.keys())
+        out[name + "_keys"] = np.array(keys)
+        out[name + "_probs"] = np.array([res[k] for k in keys], dtype=np.float64)
+        out[name + "_ref_seconds"] = np.float64(secs)
+        names.append(name)
+        print(name, "qubits", len(qc.qubits), "instructions", len(qc.data), "outcomes", len(keys), "reference run()", round(secs, 2), "s")
+    be.default_run = orig
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "shor.npz"), **out)
+    print("shor.npz:", names)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # python make_golden.py cif shor: only the named fixtures
+        for what in sys.argv[1:]:
+            globals()["make_" + what]()
+        sys.exit(0)
     make_gates()
     make_statevector()
     make_run()
     make_programs()
+    make_cif()
+    make_shor()
     make_fusion()

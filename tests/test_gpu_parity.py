@@ -156,7 +156,7 @@ def test_medium_width_against_oracle(sim):
 # ---------------------------------------------------------------------------------------
 
 
-@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz"])
+@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz", "cif.npz"])
 def test_run_matches_reference_results(golden_dir, sim, fixture):
     g = load(golden_dir, fixture)
     for case in g["cases"]:
@@ -270,6 +270,56 @@ def test_full_size_30_qubits_properties():
     assert set(int(o) for o in outs) <= {0, (1 << n) - 1}
 
 
+def ghz_qft_closed_form(n, y):
+    """<y| QFT (|0..0> + |1..1>)/sqrt(2): 2**(-(n+1)/2) * (1 + exp(2 pi i y (2**n - 1) / 2**n)) for the textbook
+    QFT of qrisp_b200.circuit.qft_circuit (final swaps included; the index has qubit 0 as its most
+    significant bit).  Checked against the oracle in the test below before it is trusted."""
+    y = np.asarray(y, dtype=np.float64)
+    return 2.0 ** (-(n + 1) / 2) * (1.0 + np.exp(-2j * np.pi * y / 2.0**n))
+
+
+def test_closed_form_of_ghz_qft_against_the_oracle():
+    n = 10
+    want = ref_sim.statevector(ghz_qft_circuit(n), dtype=np.complex128)
+    np.testing.assert_allclose(ghz_qft_closed_form(n, np.arange(1 << n)), want, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [30, 33])
+def test_full_size_ghz_qft_matches_the_closed_form(n):
+    """BASELINE.json configs[1] (30 qubits) and the widest single-GPU register (33 qubits, 64 GiB): amplitudes
+    at random basis states against the closed form, within 1e-5 RELATIVE to the amplitude scale 2**(-n/2)
+    (the absolute north-star tolerance would be vacuous at this width), and a chi-square of device
+    samples against the closed-form distribution, labels bit-exact."""
+    import torch
+
+    from qrisp_b200.engine import StateVector
+
+    free, _total = torch.cuda.mem_get_info()
+    if free < (8 << n) + (2 << 30):
+        pytest.skip(f"needs {(8 << n) >> 30} GiB of device memory")
+    sv = StateVector(n)
+    sv.apply_circuit([i for i in ghz_qft_circuit(n).data if i.matrix is not None])
+    assert abs(sv.norm2() - 1.0) < 1e-5
+    rng = np.random.default_rng(n)
+    idx = np.concatenate([rng.integers(0, 1 << n, 2000, dtype=np.uint64), np.array([0, 1, 2, (1 << n) - 1, 1 << (n - 1)], dtype=np.uint64)])
+    got = sv.amplitudes(idx)
+    want = ghz_qft_closed_form(n, idx)
+    scale = 2.0 ** (-n / 2)
+    assert np.abs(got - want).max() < 1e-5 * scale, np.abs(got - want).max() / scale
+    # distribution: p(y) = 2**-n (1 + cos(2 pi y / 2**n)); 64 bins over the top 6 outcome bits
+    shots = 200_000
+    outs = sv.sample(shots, list(range(n)), rng=np.random.default_rng(7))
+    assert outs.max() < (1 << n)
+    bins = (outs >> np.uint64(n - 6)).astype(np.int64)
+    hist = np.bincount(bins, minlength=64)
+    edges = np.arange(65) / 64.0
+    cdf = edges + np.sin(2 * np.pi * edges) / (2 * np.pi)  # integral of 1 + cos(2 pi x)
+    expect = shots * np.diff(cdf)
+    keep = expect > 5
+    chi2 = float(((hist[keep] - expect[keep]) ** 2 / expect[keep]).sum()) + float(hist[~keep].sum())
+    assert chi2 < 120, chi2  # 63 degrees of freedom: P(chi2 > 120) ~ 1e-5
+
+
 def test_multi_gpu_sharded_path():
     """Needs >= 2 GPUs on the box: launches tests/dist_gpu_check.py under torchrun."""
     import subprocess
@@ -297,6 +347,27 @@ def test_backend_object_and_apply_matrix(sim):
     got = be.run(qc, None)
     want = ref_sim.run(qc, None)
     assert set(got) == set(want) and max(abs(got[k] - want[k]) for k in got) < ATOL64
+    # the reference's Backend contract (backend.py:217-330, qrisp_simulator_backend.py:33-110): run_async ->
+    # a job that is done when it is handed out -> result().all_counts, one dict per circuit; a sequence of
+    # circuits, per-circuit shots, options
+    assert be.options == {"shots": None, "token": ""}
+    job = be.run_async(qc)
+    assert job.status() == "done" and job.cancel() is False
+    assert job.result().num_circuits == 1 and job.result().get_counts() == got
+    qc2 = random_circuit(9, 3, seed=2)
+    qc2.measure(list(range(9)))
+    both = be.run([qc, qc2], 500)
+    assert isinstance(both, list) and len(both) == 2 and all(sum(d.values()) == 500 for d in both)
+    per = be.run_async([qc, qc2], [100, 300]).result().all_counts
+    assert [sum(d.values()) for d in per] == [100, 300]
+    be.update_options(shots=64)
+    assert sum(be.run(qc).values()) == 64
+    with pytest.raises(AttributeError):
+        be.update_options(nonsense=1)
+    with pytest.raises(ValueError):
+        be.run(qc, -5)
+    # keyword compatibility with qrisp.simulator.run(qc, shots, token, iqs, insert_reset)
+    assert sim.run(qc, None, "", None, True) == got and sim.run(qc, None, insert_reset=False) == got
     sv = StateVector(6)
     rng = np.random.default_rng(0)
     a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
@@ -304,6 +375,108 @@ def test_backend_object_and_apply_matrix(sim):
     sv.apply_matrix(u, (4, 1))
     want = ref_sim.apply_matrix(ref_sim.zero_state(6), u, (4, 1), 6, threshold=False)
     np.testing.assert_allclose(sv.statevector(), want, atol=ATOL64)
+
+
+def test_qrisp_default_backend_on_the_b200(golden_dir):
+    """BASELINE.json configs[0] end to end through Qrisp itself: with the vendored reference (oracle/_ref, see
+    oracle/build_ref.py) importable, ``QuantumFloat(20)``, ``h``, ``QFT(inv=True)``, ``get_measurement()`` runs on
+    the B200 backend installed as ``qrisp.default_backend.def_backend`` and gives what the reference's own
+    simulator gave when the fixture was recorded."""
+    from oracle import refstub
+
+    qrisp = refstub.import_reference()
+    if qrisp is None:
+        pytest.skip("oracle/_ref is not built (python oracle/build_ref.py, in the build container)")
+    import qrisp.default_backend as db
+    from qrisp import QFT, QuantumFloat, h
+
+    from qrisp_b200.backend import make_qrisp_backend
+
+    g = np.load(os.path.join(golden_dir, "programs.npz"))
+    old = db.def_backend
+    db.def_backend = make_qrisp_backend()
+    try:
+        for size in (6, 20):
+            qf = QuantumFloat(size)
+            h(qf)
+            QFT(qf, inv=True)
+            mes = dict(qf.get_measurement(backend=db.def_backend))
+            want = dict(zip((float(k) for k in g[f"qfloat_h_iqft{size}_decoded_keys"]), (float(v) for v in g[f"qfloat_h_iqft{size}_decoded_probs"])))
+            assert set(float(k) for k in mes) == set(want), size
+            assert max(abs(float(mes[k]) - want[float(k)]) for k in mes) < 1e-5
+    finally:
+        db.def_backend = old
+
+
+def test_sparse_start_and_program_replay(sim):
+    """The host prefix (qb2_sparse_prefix) in front of the dense sweeps: any cut gives the same state; a
+    compiled program replays from a reset and refuses a map it was not compiled for."""
+    from qrisp_b200 import _lib
+    from qrisp_b200.engine import StateVector
+
+    for qc in (ghz_qft_circuit(15), random_circuit(14, 5, seed=3, two_qubit="cx")):
+        want = ref_sim.statevector(qc)
+        instrs = [i for i in qc.data if i.matrix is not None]
+        for support in (0, 1, 2, 16, 300, 1024):
+            sv = StateVector(qc.num_qubits, prefix_support=support)
+            sv.apply_circuit(instrs)
+            np.testing.assert_allclose(sv.statevector(), want, atol=ATOL64, err_msg=f"support {support}")
+            if support == 0:
+                assert sv.stats.get("prefix_gates", 0) == 0
+        sv = StateVector(qc.num_qubits)
+        prog = sv.compile(instrs)
+        for _ in range(2):
+            sv.reset()
+            prog.run()
+            np.testing.assert_allclose(sv.statevector(), want, atol=ATOL64)
+        with pytest.raises(_lib.Qb2Error):
+            prog.run()  # the state is written and the map has moved: not what the program was compiled for
+    # a circuit that the prefix finishes alone: nothing is launched until somebody looks at the state
+    sv = StateVector(12)
+    sv.apply_circuit([i for i in ghz_circuit(12).data if i.matrix is not None])
+    assert sv.stats["passes"] == 0 and sv._pending is not None
+    st = sv.statevector()
+    assert abs(st[0] - 2**-0.5) < 1e-6 and abs(st[-1] - 2**-0.5) < 1e-6 and np.count_nonzero(st) == 2
+
+
+def test_tma_kernel_matches_the_register_pipelined_kernel(sim):
+    """Same circuits through pass_kernel_tma and pass_kernel: both against the oracle."""
+    from qrisp_b200.engine import StateVector
+
+    for seed, n in ((1, 13), (2, 16), (3, 19)):
+        qc = random_circuit(n, 4, seed=seed, two_qubit="cx" if seed % 2 else "cz")
+        qft_circuit(n, qc)
+        want = ref_sim.statevector(qc)
+        instrs = [i for i in qc.data if i.matrix is not None]
+        used = {}
+        for tma in (True, False):
+            sv = StateVector(n, tma=tma, prefix_support=0)
+            steps = sv.apply_circuit(instrs)
+            used[tma] = sum(1 for s in steps if getattr(s, "tma", False))
+            np.testing.assert_allclose(sv.statevector(), want, atol=ATOL64, err_msg=f"tma={tma} n={n}")
+        assert used[True] > 0 and used[False] == 0
+
+
+def test_shor_find_order_at_the_named_sizes(golden_dir, sim):
+    """BASELINE.json configs[2]: the README's ``find_order`` for N = 35 and N = 77, circuits as Qrisp compiled
+    them (tests/golden/make_golden.py make_shor), through ``run()``: labels and probabilities equal the
+    reference's."""
+    path = os.path.join(golden_dir, "shor.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/shor.npz not generated")
+    import time
+
+    g = np.load(path)
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        t0 = time.perf_counter()
+        got = sim.run(qc, None)
+        secs = time.perf_counter() - t0
+        ref = {str(k): float(p) for k, p in zip(g[case + "_keys"], g[case + "_probs"])}
+        assert set(got) == set(ref), (case, len(got), len(ref))
+        assert max(abs(got[k] - ref[k]) for k in ref) < 1e-5, case
+        print(f"{case}: {qc.num_qubits} qubits, {len(qc.data)} instructions: B200 run() {secs:.2f} s, reference {float(g[case + '_ref_seconds']):.2f} s")
 
 
 @pytest.mark.parametrize("switch", ["QB2_NO_SLOTS", "QB2_NO_CHAIN", "QB2_NO_HAD", "QB2_NO_RELABEL", "QB2_NO_BFLY"])

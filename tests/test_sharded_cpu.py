@@ -50,7 +50,7 @@ def _worker(rank, world, port, case, out_dir):
             def _sparse_for(self, step, state):
                 from qrisp_b200 import prefix
 
-                phys = prefix.to_physical(state[0], self.pos, len(self.pos))
+                phys = prefix.to_physical(state[0], self._pending_map(), len(self.pos))
                 data, k = prefix.sparse_input_list(step, phys, state[1], self.n, self.hi_base, np.complex64)
                 pad = (4 * k + 15) // 16 * 16
                 return (np.frombuffer(data, np.uint32, k, 0), np.frombuffer(data, np.uint32, k, pad),
@@ -59,7 +59,7 @@ def _worker(rank, world, port, case, out_dir):
             def _init_sparse(self, state):
                 from qrisp_b200 import prefix
 
-                phys = prefix.to_physical(state[0], self.pos, len(self.pos))
+                phys = prefix.to_physical(state[0], self._pending_map(), len(self.pos))
                 mine = (phys >> np.uint64(self.n)) == np.uint64(self.rank)
                 st = np.zeros(1 << self.n, dtype=np.complex64)
                 st[(phys[mine] & np.uint64((1 << self.n) - 1)).astype(np.int64)] = state[1][mine].astype(np.complex64)
