@@ -3,7 +3,7 @@ NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude -Iqrisp_b200/csrc $(EXTRA)
 CSRC      := qrisp_b200/csrc
-SRC       := $(CSRC)/qb2_api.cu $(CSRC)/qb2_pass.cu $(CSRC)/qb2_measure.cu $(CSRC)/qb2_prefix.cu
+SRC       := $(CSRC)/qb2_api.cu $(CSRC)/qb2_pass.cu $(CSRC)/qb2_measure.cu $(CSRC)/qb2_prefix.cu $(CSRC)/qb2_block_tc.cu
 # one translation unit per pass-kernel variant (qb2_pass_inst.cu with -DQB2_INST=k): they build in parallel
 INST      := 0 1 2 3 4 5 6 7 8 9 10 11 12 13
 INSTOBJ   := $(foreach k,$(INST),$(CSRC)/qb2_pass_inst_$(k).o)

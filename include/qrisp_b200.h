@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QB2_ABI_VERSION 7
+#define QB2_ABI_VERSION 8
 
 #define QB2_C64 0
 #define QB2_C128 1
@@ -126,6 +126,19 @@ int qb2_run_pass(void *state, int n, uint64_t hi_base, const void *header, const
 int qb2_apply_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev,
                          const int *targets, int k, uint64_t ctrl_mask, uint64_t ctrl_value, int dtype,
                          void *stream);
+
+/* Dense 5-qubit block on the tensor cores (tcgen05.mma, TF32 x 3 split, accumulators in TMEM): the fast
+ * path for the reference's grouped unitaries (circuit_preprocessing.py:119-157 `group_qc` ->
+ * tensor_factor.py:67-89 `apply_matrix`) at k = 5, complex64, n >= 12 local qubits.  IN PLACE.
+ * `targets`: 5 ascending local positions, matrix index bit i <-> targets[i]; controls over the physical
+ * index as in a pass.  `block_dev`: DEVICE copy of the 32 KB that qb2_pack_block_tc wrote. */
+#define QB2_BLOCK_TC_QUBITS 5
+#define QB2_BLOCK_TC_BYTES 32768
+int qb2_apply_block_tc(void *state, int n, uint64_t hi_base, const void *block_dev, const int *targets,
+                       uint64_t ctrl_mask, uint64_t ctrl_value, void *stream);
+/* Host only: a 32 x 32 unitary (complex128, row-major, interleaved re/im) -> the two TF32 halves of the real
+ * 64 x 64 operand in the kernel's shared-memory layout (QB2_BLOCK_TC_BYTES bytes at `out_host`). */
+int qb2_pack_block_tc(const void *matrix_c128_host, void *out_host);
 
 /* ---------------------------------------------------------------- layout
  * dst[j] = src[i] where bit perm[p] of j = bit p of i (out of place).  Used to return a

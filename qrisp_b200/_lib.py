@@ -13,7 +13,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libqb2.so")
 
-QB2_ABI_VERSION = 7
+QB2_ABI_VERSION = 8
+QB2_BLOCK_TC_BYTES = 32768  # include/qrisp_b200.h
 QB2_C64, QB2_C128 = 0, 1
 QB2_NO_BASIS = (1 << 64) - 1
 
@@ -46,6 +47,11 @@ SYMBOLS = {
         [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_int, _c.c_uint64,
          _c.c_uint64, _c.c_int, _c.c_void_p],
     ),
+    "qb2_apply_block_tc": (
+        _c.c_int,
+        [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_uint64, _c.c_uint64, _c.c_void_p],
+    ),
+    "qb2_pack_block_tc": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     "qb2_permute_bits": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.POINTER(_c.c_int), _c.c_int, _c.c_void_p]),
     "qb2_norm2": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "qb2_probabilities": (

@@ -121,6 +121,17 @@ int qb2_apply_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, co
                              (cudaStream_t)stream);
 }
 
+int qb2_apply_block_tc(void *state, int n, uint64_t hi_base, const void *block_dev, const int *targets,
+                       uint64_t ctrl_mask, uint64_t ctrl_value, void *stream) {
+    if (!state || !block_dev || !targets) return set_error(QB2_EINVAL, "qb2_apply_block_tc: null pointer");
+    return launch_block_tc(state, n, hi_base, block_dev, targets, ctrl_mask, ctrl_value, (cudaStream_t)stream);
+}
+
+int qb2_pack_block_tc(const void *matrix_c128_host, void *out_host) {
+    if (!matrix_c128_host || !out_host) return set_error(QB2_EINVAL, "qb2_pack_block_tc: null pointer");
+    return pack_block_tc(reinterpret_cast<const double *>(matrix_c128_host), reinterpret_cast<float *>(out_host));
+}
+
 int qb2_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, void *stream) {
     if (int rc = check_dtype(dtype, "qb2_permute_bits")) return rc;
     return launch_permute_bits(src, dst, n, perm, dtype, (cudaStream_t)stream);

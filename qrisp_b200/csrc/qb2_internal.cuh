@@ -76,6 +76,9 @@ int launch_init_sparse(void *state, int n, const uint64_t *idx_dev, const void *
 int launch_init_basis(void *state, int n, uint64_t basis, int dtype, cudaStream_t s);
 int launch_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev, const int *targets,
                       int k, uint64_t cmask, uint64_t cval, int dtype, cudaStream_t s);
+int launch_block_tc(void *state, int n, uint64_t hi_base, const void *gate_dev, const int *targets, uint64_t cmask, uint64_t cval,
+                    cudaStream_t s);
+int pack_block_tc(const double *u, float *out);
 int launch_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, cudaStream_t s);
 int launch_norm2(const void *state, int n, double *out_dev, int dtype, cudaStream_t s);
 int launch_probabilities(const void *state, int n, uint64_t hi_base, const int *mes_pos, int m, double *probs_dev,

@@ -10,6 +10,7 @@ multi-gate passes.  PyTorch is used for buffer ownership, streams and (multi-GPU
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -154,10 +155,35 @@ class DeviceOps:
             self.stats["gate_ops"] += consumed
         return instructions[consumed:]
 
+    def _run_block_tc(self, s):
+        """A dense 5-qubit block on the tensor cores (qb2_apply_block_tc: tcgen05.mma, TF32 x 3), in place."""
+        order = np.argsort(s.positions)
+        positions = [int(s.positions[i]) for i in order]
+        old = np.arange(32)
+        new = np.zeros(32, dtype=np.int64)  # matrix index after sorting the targets by position
+        for j in range(5):
+            new |= ((old >> int(order[j])) & 1) << j
+        m = np.empty((32, 32), dtype=np.complex128)
+        m[np.ix_(new, new)] = np.asarray(s.matrix, dtype=np.complex128)
+        packed = np.empty(_lib.QB2_BLOCK_TC_BYTES // 4, dtype=np.float32)
+        _lib.check(self.lib.qb2_pack_block_tc(np.ascontiguousarray(m).ctypes.data, packed.ctypes.data), "qb2_pack_block_tc")
+        dev = self._upload_bytes(packed.tobytes())
+        tg = (ctypes.c_int * 5)(*positions)
+        _lib.check(
+            self.lib.qb2_apply_block_tc(self._raw_state().data_ptr(), self.n, self.hi_base, dev.data_ptr(), tg, s.cmask, s.cval,
+                                        self._stream()),
+            "qb2_apply_block_tc",
+        )
+        self.stats["big"] += 1
+        self.stats["block_tc"] = self.stats.get("block_tc", 0) + 1
+
     def _run_big(self, s):
         self._materialize()
         torch = _torch()
         k = len(s.positions)
+        if (k == 5 and self.dtype == QB2_C64 and self.n >= 12 and all(p < self.n for p in s.positions)
+                and getattr(self, "block_tc", True) and os.environ.get("QB2_NO_BLOCK_TC") is None):
+            return self._run_block_tc(s)
         m = np.ascontiguousarray(s.matrix, dtype=self.np_dtype)
         m_dev = self._upload_bytes(m.tobytes())
         tg = (ctypes.c_int * k)(*s.positions)
