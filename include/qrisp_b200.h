@@ -146,6 +146,17 @@ int qb2_pack_block_tc(const void *matrix_c128_host, void *out_host);
  * TensorFactor.swap (tensor_factor.py:56-64) when data really has to move. */
 int qb2_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, void *stream);
 
+/* Qubit swap of a sharded state in ONE kernel over peer memory (NVLink / NVSwitch): the local bit permutation
+ * and the all-to-all together.  `peer_states`: HOST array of `world` DEVICE pointers, entry s = rank s's shard
+ * (2**n amplitudes each), mapped into this process (CUDA IPC; entry `rank` is the local shard).  Rank `rank`
+ * pulls dst[(s, low)] = peer_states[s][i] with bit p of i = bit perm[p] of (rank, low), (x, low) meaning x on
+ * the top log2(world) bits -- exactly what qb2_permute_bits followed by an all-to-all of 2**g contiguous
+ * chunks delivers (perm NULL = identity).  Position 0 must map to itself for complex64 (16-byte units).  The
+ * caller orders the kernel between two cross-rank barriers.  The reference has no counterpart (single
+ * process); this is the north star's "all-to-all qubit swaps over NVLink". */
+int qb2_swap_pull(void *dst, const void *const *peer_states, int world, int rank, int n, const int *perm, int dtype,
+                  void *stream);
+
 /* ---------------------------------------------------------------- measurement
  * out_dev[0] = sum |amp|^2 (double, device pointer; overwritten).  BiArray.squared_norm
  * (bi_arrays.py:1059). */

@@ -52,6 +52,10 @@ SYMBOLS = {
         [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_uint64, _c.c_uint64, _c.c_void_p],
     ),
     "qb2_pack_block_tc": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "qb2_swap_pull": (
+        _c.c_int,
+        [_c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_int, _c.c_int, _c.c_int, _c.POINTER(_c.c_int), _c.c_int, _c.c_void_p],
+    ),
     "qb2_permute_bits": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.POINTER(_c.c_int), _c.c_int, _c.c_void_p]),
     "qb2_norm2": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "qb2_probabilities": (

@@ -132,6 +132,11 @@ int qb2_pack_block_tc(const void *matrix_c128_host, void *out_host) {
     return pack_block_tc(reinterpret_cast<const double *>(matrix_c128_host), reinterpret_cast<float *>(out_host));
 }
 
+int qb2_swap_pull(void *dst, const void *const *peer_states, int world, int rank, int n, const int *perm, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_swap_pull")) return rc;
+    return launch_swap_pull(dst, peer_states, world, rank, n, perm, dtype, (cudaStream_t)stream);
+}
+
 int qb2_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, void *stream) {
     if (int rc = check_dtype(dtype, "qb2_permute_bits")) return rc;
     return launch_permute_bits(src, dst, n, perm, dtype, (cudaStream_t)stream);

@@ -39,6 +39,7 @@ int sm_count();
     } while (0)
 
 #define QB2_MAX_DEVICES 64
+#define QB2_MAX_PEERS 16
 
 // sparse input of the first pass after a reset (QB2_FEATURE_ZERO_INPUT): the listed non-zero amplitudes,
 // sorted by tile number; `loc` = (thread << r) | register under the FIRST phase's distribution
@@ -79,6 +80,7 @@ int launch_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const
 int launch_block_tc(void *state, int n, uint64_t hi_base, const void *gate_dev, const int *targets, uint64_t cmask, uint64_t cval,
                     cudaStream_t s);
 int pack_block_tc(const double *u, float *out);
+int launch_swap_pull(void *dst, const void *const *peers, int world, int rank, int n, const int *perm, int dtype, cudaStream_t s);
 int launch_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, cudaStream_t s);
 int launch_norm2(const void *state, int n, double *out_dev, int dtype, cudaStream_t s);
 int launch_probabilities(const void *state, int n, uint64_t hi_base, const int *mes_pos, int m, double *probs_dev,

@@ -36,6 +36,46 @@ __global__ void permute_bits_kernel(const vec *__restrict__ src, vec *__restrict
         dst[j] = src[apply_runs(runs, j)];
 }
 
+// ------------------------------------------------------------------ qubit swap over peer memory
+// One kernel = the local bit permutation AND the all-to-all of a qubit swap: every rank PULLS its new shard
+// straight out of its peers' HBM (NVLink / NVSwitch peer mappings).  Destination index j = (s, low) with s the
+// top g bits: the 16-byte unit comes from rank s, index runs((rank, low)) -- what
+// permute_bits followed by all_to_all_single would have delivered, without the extra HBM pass on the sender
+// and without a staging copy.  Units of 16 bytes: the lowest positions are never evicted, so they stay put.
+struct PeerPtrs {
+    const uint4 *p[QB2_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256)
+    swap_pull_kernel(const PeerPtrs peers, uint4 *__restrict__ dst, const uint64_t units, const int low_bits,
+                     const uint64_t rank_hi, const BitRuns runs, const int first_peer) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t low_mask = (1ull << low_bits) - 1ull;
+    const uint64_t peer_mask = (units >> low_bits) - 1ull;
+    constexpr int U = 4;  // loads in flight per thread: NVLink round trips are long
+    // (peers are visited starting with the one after this rank, so the ranks do not all hit the same source at once)
+    for (uint64_t k0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k0 < units; k0 += U * stride) {
+        uint4 v[U];
+        uint64_t d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t k = k0 + (uint64_t)u * stride;
+            if (k < units) {
+                const uint64_t s = ((k >> low_bits) + (uint64_t)first_peer) & peer_mask;
+                const uint64_t low = k & low_mask;
+                const uint4 *src = peers.p[s] + apply_runs(runs, rank_hi | low);
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
+                             : "l"(src));
+                d[u] = (s << low_bits) | low;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (k0 + (uint64_t)u * stride < units) dst[d[u]] = v[u];
+    }
+}
+
 // ------------------------------------------------------------------ norm2
 __device__ __forceinline__ double block_sum(double v, double *sh) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -326,6 +366,46 @@ unsigned grid_for(uint64_t items, unsigned threads, unsigned per_sm) {
 }
 
 }  // namespace
+
+int launch_swap_pull(void *dst, const void *const *peers, int world, int rank, int n, const int *perm, int dtype, cudaStream_t s) {
+    int g = 0;
+    while ((1 << g) < world) ++g;
+    const int unit_bits = dtype == QB2_C64 ? 1 : 0;  // amplitudes per 16-byte unit, as a bit count
+    if (!dst || !peers || world < 2 || world > QB2_MAX_PEERS || (1 << g) != world || rank < 0 || rank >= world || n < g + 2 || n > 40)
+        return set_error(QB2_EINVAL, "qb2_swap_pull: bad arguments");
+    // index transform in amplitudes: bit p of the source index = bit perm[p] of (rank, low); identity when perm is NULL
+    int pm[40];
+    uint64_t seen = 0;
+    for (int p = 0; p < n; ++p) {
+        pm[p] = perm ? perm[p] : p;
+        if (pm[p] < 0 || pm[p] >= n || ((seen >> pm[p]) & 1)) return set_error(QB2_EINVAL, "qb2_swap_pull: not a permutation");
+        seen |= 1ull << pm[p];
+    }
+    if (unit_bits && pm[0] != 0) return set_error(QB2_EINVAL, "qb2_swap_pull: position 0 must stay in place (16-byte units)");
+    BitRuns r;  // in 16-byte units: drop the lowest amplitude bit of a complex64 state
+    r.n = 0;
+    int p = unit_bits;
+    while (p < n) {
+        int len = 1;
+        while (p + len < n && pm[p + len] == pm[p] + len) ++len;
+        r.src[r.n] = (uint8_t)(pm[p] - unit_bits);
+        r.dst[r.n] = (uint8_t)(p - unit_bits);
+        r.len[r.n] = (uint8_t)len;
+        ++r.n;
+        p += len;
+    }
+    PeerPtrs pp;
+    for (int k = 0; k < world; ++k) {
+        if (!peers[k]) return set_error(QB2_EINVAL, "qb2_swap_pull: null peer pointer");
+        pp.p[k] = reinterpret_cast<const uint4 *>(peers[k]);
+    }
+    const int nu = n - unit_bits;  // bits of a unit index
+    const uint64_t units = 1ull << nu;
+    const unsigned grid = grid_for(units, 256, 16);
+    swap_pull_kernel<<<grid, 256, 0, s>>>(pp, reinterpret_cast<uint4 *>(dst), units, nu - g, (uint64_t)rank << (nu - g), r, rank + 1);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "swap_pull launch");
+}
 
 int launch_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, cudaStream_t s) {
     if (!src || !dst || !perm || n < 1 || n > 40 || src == dst)

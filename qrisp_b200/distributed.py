@@ -140,6 +140,64 @@ class ShardedStateVector(DeviceOps):
 
         torch.cuda.current_stream(self.device).synchronize()
 
+    # ------------------------------------------------------------------ peer memory (NVLink / NVSwitch)
+    def _peer_setup(self):
+        """Map every rank's two shard buffers into this process (CUDA IPC through torch's storage sharing)
+        so that a qubit swap can pull straight out of the peers' HBM (qb2_swap_pull).  Returns False when
+        that is not possible here (no peer access, QB2_NO_PEER_SWAP set): the NCCL path takes over."""
+        if getattr(self, "_peers", None) is not None:
+            return bool(self._peers)
+        self._peers = {}
+        if os.environ.get("QB2_NO_PEER_SWAP") is not None or self.device.type != "cuda":
+            return False
+        import torch
+
+        try:
+            mine = [self.state.untyped_storage()._share_cuda_(), self._scratch.untyped_storage()._share_cuda_()]
+            ptrs = [self.state.data_ptr(), self._scratch.data_ptr()]
+            everyone = [None] * self.world
+            self.dist.all_gather_object(everyone, (self.rank, mine), group=self.group)
+            keep, table = [], {0: [None] * self.world, 1: [None] * self.world}
+            for r, infos in everyone:
+                for k, info in enumerate(infos):
+                    if r == self.rank:
+                        table[k][r] = ptrs[k]
+                        continue
+                    # opened with THIS rank's device current: cudaIpcOpenMemHandle then maps the peer's memory
+                    # for this device (lazy peer access), which is what the pulling kernel needs
+                    st = torch.UntypedStorage._new_shared_cuda(self.device.index, *info[1:])
+                    keep.append(st)
+                    table[k][r] = st.data_ptr()
+            ok = torch.tensor([1], device=self.device)
+            self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+            self._peer_keep = keep
+            self._peers = {ptrs[0]: table[0], ptrs[1]: table[1]}
+            self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        except Exception as exc:  # noqa: BLE001 -- any failure means "use NCCL", and says so once
+            import warnings
+
+            warnings.warn(f"qrisp_b200: peer-memory qubit swaps unavailable ({exc!r}); using NCCL all_to_all")
+            self._peers = {}
+        return bool(self._peers)
+
+    def _stream_barrier(self):
+        """Every rank's stream has reached this point when the tiny all-reduce completes (stream ordered)."""
+        self.dist.all_reduce(self._flag, group=self.group)
+
+    def _swap_pull(self, perm):
+        """Local permutation + all-to-all of a qubit swap in one kernel over peer memory."""
+        self._materialize()
+        table = self._peers[self.state.data_ptr()]
+        peers = (ctypes.c_void_p * self.world)(*table)
+        arr = (ctypes.c_int * self.n)(*perm) if perm is not None else None
+        self._stream_barrier()  # the peers' shards are complete
+        _lib.check(
+            self.lib.qb2_swap_pull(self._scratch.data_ptr(), peers, self.world, self.rank, self.n, arr, self.dtype, self._stream()),
+            "qb2_swap_pull",
+        )
+        self._stream_barrier()  # nobody overwrites a shard a peer is still reading
+        self.state, self._scratch = self._scratch, self.state
+
     # ------------------------------------------------------------------ planning
     def compile(self, instructions):
         """Host prefix on the pending sparse state, then plan with swaps (every rank computes the same)."""
@@ -224,9 +282,13 @@ class ShardedStateVector(DeviceOps):
 
     # ------------------------------------------------------------------ execution of one swap
     def run_swap(self, step):
-        if step.perm is not None:
-            self._permute_local(step.perm)
-        self._all_to_all()
+        if self._peer_setup() and (step.perm is None or self.dtype == QB2_C128 or step.perm[0] == 0):
+            self._swap_pull(step.perm)
+            self.stats["peer_swaps"] = self.stats.get("peer_swaps", 0) + 1
+        else:
+            if step.perm is not None:
+                self._permute_local(step.perm)
+            self._all_to_all()
         self.stats["swaps"] += 1
 
     # ------------------------------------------------------------------ read-out
