@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256)
                 const uint64_t s = ((k >> low_bits) + (uint64_t)first_peer) & peer_mask;
                 const uint64_t low = k & low_mask;
                 const uint4 *src = peers.p[s] + apply_runs(runs, rank_hi | low);
-                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w)
                              : "l"(src));
                 d[u] = (s << low_bits) | low;
@@ -209,26 +209,81 @@ __global__ void __launch_bounds__(SAMPLE_THREADS)
     }
 }
 
-// single CTA, in-place inclusive scan
-__global__ void __launch_bounds__(1024) scan_kernel(double *__restrict__ v, const uint64_t n) {
-    __shared__ double part[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t per = (n + 1023) / 1024;
-    const uint64_t lo = tid * per, hi = (lo + per < n) ? lo + per : n;
-    double acc = 0;
-    for (uint64_t i = lo; i < hi; ++i) acc += v[i];
-    part[tid] = acc;
-    __syncthreads();
-    for (uint32_t o = 1; o < 1024; o <<= 1) {
-        const double add = (tid >= o) ? part[tid - o] : 0.0;
-        __syncthreads();
-        part[tid] += add;
-        __syncthreads();
+// in-place inclusive scan of the chunk sums over many CTAs: block totals, a scan of the totals by one CTA,
+// then every block scans its own 2048 entries on top of its offset (coalesced, double accumulation)
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_PER_THREAD;
+constexpr int SCAN_MAX_BLOCKS = 1 << 16;  // scanned by one CTA in the middle step
+
+__device__ __forceinline__ double block_scan_exclusive(const double v, double *sh, double &total) {
+    // exclusive scan of one value per thread over a CTA of SCAN_THREADS threads; `total` on every thread
+    double x = v;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
     }
-    double run = (tid > 0) ? part[tid - 1] : 0.0;
-    for (uint64_t i = lo; i < hi; ++i) {
-        run += v[i];
-        v[i] = run;
+    if (lane == 31) sh[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < SCAN_THREADS / 32 ? sh[lane] : 0.0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        if (lane < SCAN_THREADS / 32) sh[lane] = t;
+    }
+    __syncthreads();
+    const double before = w > 0 ? sh[w - 1] : 0.0;
+    total = sh[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+    return before + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_totals_kernel(const double *__restrict__ v, const uint64_t n, double *__restrict__ totals) {
+    __shared__ double sh[32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK;
+    double acc = 0;
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        const uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) acc += v[i];
+    }
+    double total;
+    block_scan_exclusive(acc, sh, total);
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(double *__restrict__ totals, const uint32_t nblocks) {
+    // exclusive scan of the block totals, in place, by one CTA (at most SCAN_MAX_BLOCKS entries)
+    __shared__ double sh[32];
+    double run = 0;
+    for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const double x = i < nblocks ? totals[i] : 0.0;
+        double total;
+        const double ex = block_scan_exclusive(x, sh, total);
+        if (i < nblocks) totals[i] = run + ex;
+        run += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(double *__restrict__ v, const uint64_t n, const double *__restrict__ offsets) {
+    __shared__ double sh[32];
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_PER_THREAD;
+    double x[SCAN_PER_THREAD];
+    double acc = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        x[k] = base + k < n ? v[base + k] : 0.0;
+        acc += x[k];
+    }
+    double total;
+    double run = offsets[blockIdx.x] + block_scan_exclusive(acc, sh, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; ++k) {
+        run += x[k];
+        if (base + k < n) v[base + k] = run;
     }
 }
 
@@ -484,6 +539,24 @@ int sample_chunk_bits(int n) {
     return cb;
 }
 
+// in-place inclusive scan of `n` doubles; the block offsets live in a small per-device scratch buffer
+static int launch_scan(double *v, uint64_t n, cudaStream_t s) {
+    static double *scratch[QB2_MAX_DEVICES] = {nullptr};
+    int dev = 0;
+    QB2_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= QB2_MAX_DEVICES) return set_error(QB2_ELIMIT, "device ordinal %d outside the engine's table", dev);
+    const uint64_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if (nblocks > (uint64_t)SCAN_MAX_BLOCKS) return set_error(QB2_ELIMIT, "scan of %llu entries", (unsigned long long)n);
+    if (!scratch[dev]) QB2_CUDA(cudaMalloc(&scratch[dev], SCAN_MAX_BLOCKS * sizeof(double)));
+    scan_totals_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(v, n, scratch[dev]);
+    scan_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(scratch[dev], (uint32_t)nblocks);
+    scan_apply_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, s>>>(v, n, scratch[dev]);
+    count_launch();
+    count_launch();
+    count_launch();
+    return check_cuda(cudaGetLastError(), "scan launch");
+}
+
 int launch_sample_prepare(const void *state, int n, double *chunk_sums_dev, int dtype, cudaStream_t s) {
     if (!state || !chunk_sums_dev || n < 0 || n > 40) return set_error(QB2_EINVAL, "qb2_sample_prepare: bad arguments");
     const int cb = sample_chunk_bits(n);
@@ -497,9 +570,7 @@ int launch_sample_prepare(const void *state, int n, double *chunk_sums_dev, int 
         chunk_sums_kernel<double2><<<(unsigned)blocks, SAMPLE_THREADS, 0, s>>>((const double2 *)state, cb, nchunks, chunk_sums_dev);
     count_launch();
     QB2_CUDA(cudaGetLastError());
-    scan_kernel<<<1, 1024, 0, s>>>(chunk_sums_dev, nchunks);
-    count_launch();
-    return check_cuda(cudaGetLastError(), "sample_prepare launch");
+    return launch_scan(chunk_sums_dev, nchunks, s);
 }
 
 int launch_sample_draw(const void *state, int n, const double *chunk_sums_dev, const double *uniforms_dev,

@@ -66,6 +66,12 @@ def unitarize(circuit):
                 nxt = stream[look]
                 if q in nxt.qubits:
                     if nxt.name == "reset":
+                        # NOTE (pinned by tests/test_planner_cpu.py::test_reset_is_hoisted_over_z_commuting_gates):
+                        # the reset is taken out of the stream HERE, i.e. it moves in front of the gates in
+                        # between, all of which commute with Z on q.  A gate that q only CONTROLS (measure q;
+                        # cx(q, r); reset q) therefore sees q after the reset and never fires -- exactly what the
+                        # reference's insert_multiverse_measurements does (circuit_preprocessing.py:755-789:
+                        # the same look-ahead, `reset_follows` + `instructions.pop`); kept for parity.
                         reset_follows = True
                         del stream[look]
                         is_terminal = False

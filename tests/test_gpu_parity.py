@@ -458,17 +458,20 @@ def test_tma_kernel_matches_the_register_pipelined_kernel(sim):
 
 
 def test_shor_find_order_at_the_named_sizes(golden_dir, sim):
-    """BASELINE.json configs[2]: the README's ``find_order`` for N = 35 and N = 77, circuits as Qrisp compiled
-    them (tests/golden/make_golden.py make_shor), through ``run()``: labels and probabilities equal the
-    reference's."""
+    """BASELINE.json configs[2]: the README's ``find_order`` for N = 35 (30 qubits, 16150 instructions), circuit as
+    Qrisp compiled it (tests/golden/make_golden.py make_shor), through ``run()``: labels and probabilities equal
+    the reference's.  (N = 77 -- 34 qubits, beyond the reference's own simulator -- is run by tools/shor_run.py
+    and recorded under profiles/; minutes of device time do not belong into the test suite.)"""
     path = os.path.join(golden_dir, "shor.npz")
     if not os.path.exists(path):
         pytest.skip("tests/golden/shor.npz not generated")
     import time
 
     g = np.load(path)
-    for case in g["cases"]:
-        case = str(case)
+    cases = [str(c) for c in g["cases"] if str(c) + "_keys" in g.files]
+    if not cases:
+        pytest.skip("no case with a reference result in tests/golden/shor.npz")
+    for case in cases:
         qc = Circuit.from_arrays(g, case + "_")
         t0 = time.perf_counter()
         got = sim.run(qc, None)

@@ -525,6 +525,28 @@ def test_random_gate_soup_against_the_oracle():
         assert all(w == 1 for _, side, w in report if not side.startswith("tma")), (case, report)
 
 
+def test_reset_is_hoisted_over_z_commuting_gates():
+    """measure q; cx(q, r); reset q: the look-ahead of the reference's insert_multiverse_measurements
+    (circuit_preprocessing.py:755-789) takes the reset out of the stream at the measurement, so the CX that q only
+    controls sees q AFTER the reset and never flips r.  The B200 rewriting reproduces that, and the
+    oracle -- which is pinned to the reference's results on reset circuits (run.npz) -- agrees."""
+    from oracle import ref_sim
+    from qrisp_b200.circuit import Circuit
+    from qrisp_b200.preprocess import unitarize
+
+    qc = Circuit(2, 2)
+    qc.x(0)
+    qc.measure(0, 0)
+    qc.cx(0, 1)
+    qc.append("reset", [0])
+    qc.measure(1, 1)
+    instrs, n, meas = unitarize(qc)
+    names = [i.name for i in instrs]
+    assert names.index("cx") < len(names) - 1 and n == 3  # outcome copy and reset come first, the user's CX last
+    want = ref_sim.run(qc, None)
+    assert set(want) == {"01"}, want  # clbit 0 = 1 (measured before the reset), clbit 1 = 0: r was never flipped
+
+
 def test_bench_reference_arm_prints_one_json_line():
     """bench.py --impl reference: one JSON line with the keys of the bench contract (the CPU arm runs
     without a GPU; the sample register is shrunk here to keep the test short)."""

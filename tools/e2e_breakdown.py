@@ -1,20 +1,35 @@
-import sys, time; sys.path.insert(0, '/root/repo')
+#!/usr/bin/env python
+"""Where the end-to-end time of run(qc, 4096) goes (GHZ+QFT, 30 qubits): host steps with a device
+synchronisation after each (so the sum is LARGER than the pipelined call, which is printed beside it)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
-from qrisp_b200.circuit import ghz_qft_circuit, Circuit
-from qrisp_b200 import simulator, engine
+from qrisp_b200.circuit import ghz_qft_circuit
+from qrisp_b200 import simulator, engine, prefix
+from qrisp_b200.normalize import normalize_circuit
+from qrisp_b200.planner import Planner
 from qrisp_b200.preprocess import unitarize
-n = 30
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 qc = ghz_qft_circuit(n); qc.measure(list(range(n)))
-simulator.sample_counts(qc, 16, seed=0); torch.cuda.synchronize()
+simulator.run(qc, 16, seed=0); torch.cuda.synchronize()
+sync = torch.cuda.synchronize
 for rep in range(3):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    instrs, nn, meas = unitarize(qc); t1 = time.perf_counter()
-    sv = engine.StateVector(nn); t2 = time.perf_counter()
-    sv.apply_circuit(instrs); t3 = time.perf_counter()
-    torch.cuda.synchronize(); t4 = time.perf_counter()
+    sync(); t0 = time.perf_counter()
+    simulator.run(qc, 4096, seed=rep); sync()
+    whole = time.perf_counter() - t0
+    t = [time.perf_counter()]
+    def mark(): sync(); t.append(time.perf_counter())
+    instrs, nn, meas = unitarize(qc); mark()
+    sv = engine.StateVector(nn); mark()
+    rest = sv._take_prefix(list(instrs)); mark()
+    ops = normalize_circuit(rest, max_targets=sv.cfg.max_mat, unit_tol=1e-6); mark()
+    steps, need = Planner(sv.cfg, list(sv.pos)).plan(ops); mark()
+    sv2 = engine.StateVector(nn); sv2.apply_circuit(instrs); mark()
     meas.sort(key=lambda x: -x[1]); mq = [q for q, _ in meas]
-    outs = sv.sample(4096, mq, rng=np.random.default_rng(rep)); t5 = time.perf_counter()
-    vals, counts = np.unique(outs, return_counts=True)
-    d = {bin(int(v))[2:].zfill(len(mq)): int(c) for v, c in zip(vals, counts)}; t6 = time.perf_counter()
-    print("unitarize %.2f  ctor %.2f  plan+launch %.2f  wait-for-device %.2f  sample %.2f  dict %.2f  total %.2f ms" % tuple(1e3 * x for x in (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5, t6 - t0)))
-    del sv
+    outs = sv2.sample(4096, mq, rng=np.random.default_rng(rep)); mark()
+    d = simulator.counts_dict(outs, len(mq)); mark()
+    names = ["unitarize", "ctor", "host prefix", "normalize", "plan (alone)", "ctor+apply_circuit (streamed, synced)", "sample", "counts dict"]
+    print("run() %.2f ms | " % (1e3 * whole) + "  ".join("%s %.2f" % (nm, 1e3 * (b - a)) for nm, a, b in zip(names, t, t[1:])), flush=True)
+    del sv, sv2
