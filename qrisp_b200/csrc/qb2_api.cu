@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <cuda.h>  // CUmodule / CUfunction types; entry points come from cudaGetDriverEntryPoint
+
 #include "qb2_internal.cuh"
 
 namespace qb2 {
@@ -111,6 +113,41 @@ int qb2_run_pass(void *state, int n, uint64_t hi_base, const void *header, const
     if (int rc = check_dtype(dtype, "qb2_run_pass")) return rc;
     return launch_pass(state, n, hi_base, reinterpret_cast<const qb2_pass_header *>(header), blob_dev, dtype,
                        (cudaStream_t)stream, sparse_dev, n_sparse);
+}
+
+int qb2_jit_load(const char *cubin_path, void **kernel_out) {
+    if (!cubin_path || !kernel_out) return set_error(QB2_EINVAL, "qb2_jit_load: null pointer");
+    // driver API through the runtime's entry-point lookup (no link against libcuda): the module lives in the
+    // primary context of the current device, which a runtime call makes current
+    typedef CUresult (*load_fn)(CUmodule *, const char *);
+    typedef CUresult (*getf_fn)(CUfunction *, CUmodule, const char *);
+    static load_fn mod_load = nullptr;
+    static getf_fn mod_get = nullptr;
+    if (!mod_load || !mod_get) {
+        cudaDriverEntryPointQueryResult q;
+        void *f1 = nullptr, *f2 = nullptr;
+        if (cudaGetDriverEntryPoint("cuModuleLoad", &f1, cudaEnableDefault, &q) != cudaSuccess || !f1 ||
+            cudaGetDriverEntryPoint("cuModuleGetFunction", &f2, cudaEnableDefault, &q) != cudaSuccess || !f2)
+            return set_error(QB2_ECUDA, "qb2_jit_load: the driver has no module loader");
+        mod_load = reinterpret_cast<load_fn>(f1);
+        mod_get = reinterpret_cast<getf_fn>(f2);
+    }
+    QB2_CUDA(cudaFree(nullptr));
+    CUmodule mod;
+    CUresult r = mod_load(&mod, cubin_path);
+    if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_jit_load: cuModuleLoad(%s) failed with %d", cubin_path, (int)r);
+    CUfunction fn;
+    r = mod_get(&fn, mod, "qb2_pass_jit");
+    if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_jit_load: no kernel qb2_pass_jit in %s (%d)", cubin_path, (int)r);
+    *kernel_out = (void *)fn;
+    return QB2_OK;
+}
+
+int qb2_run_pass_jit(void *kernel, void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev,
+                     void *stream, const void *sparse_dev, uint32_t n_sparse) {
+    if (!kernel) return set_error(QB2_EINVAL, "qb2_run_pass_jit: null kernel");
+    return launch_pass(state, n, hi_base, reinterpret_cast<const qb2_pass_header *>(header), blob_dev, QB2_C64,
+                       (cudaStream_t)stream, sparse_dev, n_sparse, kernel);
 }
 
 int qb2_apply_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const void *matrix_dev,

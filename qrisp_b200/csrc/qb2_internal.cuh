@@ -58,6 +58,7 @@ struct PassLaunch {
     uint32_t ntiles;
     cudaStream_t s;
     SparseInput sparse;
+    const void *jit_kernel;  // a specialised kernel of this very pass (qb2_jit_load), or null
 };
 
 // one translation unit per kernel variant (qb2_pass_inst.cu compiled with -DQB2_INST=k, see Makefile):
@@ -71,7 +72,7 @@ QB2_DECLARE_VARIANT(10) QB2_DECLARE_VARIANT(11) QB2_DECLARE_VARIANT(12) QB2_DECL
 
 // launchers implemented per translation unit
 int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, int dtype,
-                cudaStream_t s, const void *sparse_dev, uint32_t n_sparse);
+                cudaStream_t s, const void *sparse_dev, uint32_t n_sparse, const void *jit_kernel = nullptr);
 int launch_init_sparse(void *state, int n, const uint64_t *idx_dev, const void *amp_dev, uint32_t count, int dtype,
                        cudaStream_t s);
 int launch_init_basis(void *state, int n, uint64_t basis, int dtype, cudaStream_t s);

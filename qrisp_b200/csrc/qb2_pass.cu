@@ -83,7 +83,7 @@ typedef int (*variant_fn)(const PassLaunch &);
 }  // namespace
 
 int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, int dtype, cudaStream_t s,
-                const void *sparse_dev, uint32_t n_sparse) {
+                const void *sparse_dev, uint32_t n_sparse, const void *jit_kernel) {
     if (!state || !h || !blob_dev) return set_error(QB2_EINVAL, "qb2_run_pass: null pointer");
     if (h->magic != QB2_PASS_MAGIC) return set_error(QB2_EINVAL, "qb2_run_pass: bad magic 0x%08x", h->magic);
     if ((int)h->dtype != dtype) return set_error(QB2_EINVAL, "qb2_run_pass: pass dtype %d != state dtype %d", h->dtype, dtype);
@@ -110,6 +110,9 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
     L.sparse.loc = nullptr;
     L.sparse.amp = nullptr;
     L.sparse.count = 0;
+    L.jit_kernel = jit_kernel;
+    if (jit_kernel && (!(h->features & QB2_FEATURE_TMA) || dtype != QB2_C64 || h->T != 13 || h->r != 5))
+        return set_error(QB2_EINVAL, "qb2_run_pass_jit: specialised kernels exist for TMA passes only");
     if (h->features & QB2_FEATURE_ZERO_INPUT) {
         if (n_sparse > QB2_MAX_SPARSE) return set_error(QB2_ELIMIT, "qb2_run_pass: %u sparse input entries (at most %d)", n_sparse, QB2_MAX_SPARSE);
         if (n_sparse && !sparse_dev) return set_error(QB2_EINVAL, "qb2_run_pass: sparse input list missing");
@@ -133,7 +136,7 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
         if (dtype != QB2_C64 || h->T != 13 || h->r != 5)
             return set_error(QB2_EINVAL, "qb2_run_pass: QB2_FEATURE_TMA needs complex64, T=13, r=5");
         const int rc = table[12 + full](L);
-        if (rc != QB2_ELIMIT) return rc;
+        if (rc != QB2_ELIMIT || jit_kernel) return rc;
         // the tile did not fit a tensor map (or the driver lacks the encoder): the other kernel runs the
         // same pass from the same descriptors
     }

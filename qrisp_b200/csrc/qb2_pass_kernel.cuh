@@ -247,7 +247,28 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 TR(5 + 2 * p);
             }
             const uint64_t X = hi_base | xloc;
+#define QB2_SLOT_W(sl) unit_phase((frac)(sthr[(sl) * nthreads + tid] + stile[spar + (sl)]), roots)
+#define QB2_OP_DECL(name, idx) const qb2_op &name = ops[idx]
+#define QB2_PHASE_DECL(name, idx) const qb2_phase &name = phases[idx]
+#define QB2_SWITCH(x) switch (x) {
+#define QB2_CASE(c) case (c):
+#define QB2_BREAK break;
+#define QB2_DEFAULT default: break;
+#define QB2_SWITCH_END }
+#define QB2_ADVANCE(k) o += (k)
+            const uint32_t op_end = ph.first_op + ph.n_ops;
+            for (uint32_t o = ph.first_op; o < op_end; ++o) {
 #include "qb2_pass_ops.inc"
+            }
+#undef QB2_OP_DECL
+#undef QB2_PHASE_DECL
+#undef QB2_SWITCH
+#undef QB2_CASE
+#undef QB2_BREAK
+#undef QB2_DEFAULT
+#undef QB2_SWITCH_END
+#undef QB2_ADVANCE
+#undef QB2_SLOT_W
         }
         // ---- store with the last phase's distribution; load the next tile behind every store
         {

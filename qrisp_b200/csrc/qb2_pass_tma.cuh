@@ -63,11 +63,23 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap *m, const void 
 }
 __device__ __forceinline__ void group_bar(uint32_t g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1u), "n"(TMA_GROUP) : "memory"); }
 
-template <bool FULL>
-__global__ void __launch_bounds__(2 * TMA_GROUP, 1)
-    pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, const uint32_t *__restrict__ tables, const uint64_t hi_base,
-                    const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off, const uint32_t sp_off,
-                    const SparseInput SP, const __grid_constant__ PassParams P) {
+// The decode schedule of a specialised kernel (generated translation unit: qrisp_b200/jit.py); dummies here.
+#ifndef QB2_JIT_NPHASES
+#define QB2_JIT_NPHASES 1
+__host__ __device__ constexpr uint32_t jit_ndec(uint32_t) { return 0; }
+__host__ __device__ constexpr uint32_t jit_sched(uint32_t, uint32_t) { return 0; }
+__host__ __device__ constexpr qb2_op jit_op(uint32_t) { return qb2_op{}; }
+__host__ __device__ constexpr qb2_phase jit_phase(uint32_t) { return qb2_phase{}; }
+#endif
+
+// `pb`: the small section of the pass -- the by-value kernel parameter (constant bank) in the ahead-of-time
+// kernels, a const array with a known initialiser in a specialised one.  `features`: header.features as the
+// launcher wants them (QB2_FEATURE_ZERO_INPUT is decided per launch).
+template <bool FULL, bool JIT>
+__device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uint32_t *__restrict__ tables, const uint64_t hi_base,
+                                              const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off,
+                                              const uint32_t sp_off, const uint32_t inv_mask, const uint32_t features,
+                                              const SparseInput &SP, const uint8_t *const pb) {
     using real = float;
     using vec = float2;
     using frac = uint32_t;
@@ -95,7 +107,6 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
     }
     uint64_t *const full_bar = reinterpret_cast<uint64_t *>(aux + NROOT * sizeof(vec));  // [2]: one per group
 
-    const uint8_t *const pb = reinterpret_cast<const uint8_t *>(&P);
     const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(pb);
     const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(pb + H->phases_off);
     const qb2_op *const ops = reinterpret_cast<const qb2_op *>(pb + H->ops_off);
@@ -136,7 +147,12 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
     frac *const stile_all = reinterpret_cast<frac *>(aux + slot_off);                       // [2 groups][2][QB2_MAX_SLOTS]
     frac *const stile = stile_all + g * 2 * QB2_MAX_SLOTS;
     uint16_t *const slot_op = reinterpret_cast<uint16_t *>(stile_all + 4 * QB2_MAX_SLOTS);   // [QB2_MAX_SLOTS]
-    frac *const sthr = reinterpret_cast<frac *>(slot_op + QB2_MAX_SLOTS);                    // [n_slots][threads]
+    uint16_t *const slot_ofs = slot_op + QB2_MAX_SLOTS;                                      // [QB2_MAX_SLOTS]
+    // Thread parts: slot s at slot_area + slot_ofs[s] KB.  A slot whose ladders touch no bit outside the tile
+    // (bit s of inv_mask, worked out by the launcher) is the same for every tile of the pass: its unit phase is
+    // computed ONCE per CTA and kept as a float2 per thread (2 KB per slot); the other slots keep their
+    // turn fraction (1 KB per slot) and get the tile part and the root-table evaluation per tile.
+    uint8_t *const slot_area = reinterpret_cast<uint8_t *>(slot_ofs + QB2_MAX_SLOTS);
     auto ladder_sum = [&](const qb2_op &op, const uint32_t which, const uint64_t x) {
         const qb2_tab *tb = tabs + (op.kind == QB2_OP_BFLY ? (uint32_t)op.tab : (uint32_t)op.data);
         const int nthr = op.ntab_thr, nall = nthr + op.ntab_reg;
@@ -148,28 +164,45 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
     auto has_slot = [&](const qb2_op &op) {
         return op.b1 != 0 && (op.kind == QB2_OP_BFLY || op.kind == QB2_OP_DIAG_THR || op.kind == QB2_OP_DIAG_BIT);
     };
-    if (n_slots && g == 0) {
-        for (uint32_t p = 0; p < n_phases; ++p) {
-            uint64_t xt = 0;
-            for (int b = 0; b < TB; ++b)
-                if ((tid >> b) & 1u) xt |= a64[phases[p].pcol + b];
-            const uint64_t x = hi_base | xt;
-            const uint32_t op_end = phases[p].first_op + phases[p].n_ops;
-            for (uint32_t o = phases[p].first_op; o < op_end; ++o) {
-                const qb2_op &op = ops[o];
-                if (has_slot(op)) {
-                    const uint32_t ns = two_slots(op) ? 2u : 1u;
-                    for (uint32_t w = 0; w < ns; ++w) {
-                        sthr[(op.b1 - 1u + w) * nthreads + tid] = ladder_sum(op, w, x);
-                        if (tid == 0) slot_op[op.b1 - 1u + w] = (uint16_t)(o | (w << 15));
+    if (n_slots) {
+        if (threadIdx.x == 0) {
+            uint32_t kb = 0;
+            for (uint32_t sl = 0; sl < n_slots; ++sl) {
+                slot_ofs[sl] = (uint16_t)kb;
+                kb += ((inv_mask >> sl) & 1u) ? 2u : 1u;
+            }
+        }
+        __syncthreads();  // the root table and the slot offsets
+        if (g == 0) {
+            for (uint32_t p = 0; p < n_phases; ++p) {
+                uint64_t xt = 0;
+                for (int b = 0; b < TB; ++b)
+                    if ((tid >> b) & 1u) xt |= a64[phases[p].pcol + b];
+                const uint64_t x = hi_base | xt;
+                const uint32_t op_end = phases[p].first_op + phases[p].n_ops;
+                for (uint32_t o = phases[p].first_op; o < op_end; ++o) {
+                    const qb2_op &op = ops[o];
+                    if (has_slot(op)) {
+                        const uint32_t ns = two_slots(op) ? 2u : 1u;
+                        for (uint32_t w = 0; w < ns; ++w) {
+                            const uint32_t sl = op.b1 - 1u + w;
+                            const frac thr = ladder_sum(op, w, x);
+                            uint8_t *const at = slot_area + (uint32_t)slot_ofs[sl] * 1024u;
+                            if ((inv_mask >> sl) & 1u)
+                                reinterpret_cast<float2 *>(at)[tid] = unit_phase(thr, roots);
+                            else
+                                reinterpret_cast<frac *>(at)[tid] = thr;
+                            if (tid == 0) slot_op[sl] = (uint16_t)(o | (w << 15));
+                        }
                     }
                 }
             }
         }
     }
+    const uint32_t var_mask = (n_slots >= 32u ? 0xffffffffu : ((1u << n_slots) - 1u)) & ~inv_mask;  // slots with a tile part
     // ---- sparse input (first pass after a reset): tile numbers of the listed amplitudes; the landing
     // buffer is not needed for loads then and serves as the all-zero tile that empty tiles store
-    const bool zero_in = (H->features & QB2_FEATURE_ZERO_INPUT) != 0u;
+    const bool zero_in = (features & QB2_FEATURE_ZERO_INPUT) != 0u;
     uint32_t *const sp_tile = reinterpret_cast<uint32_t *>(aux + sp_off);
     if (zero_in) {
         for (uint32_t i = threadIdx.x; i < SP.count; i += blockDim.x) sp_tile[i] = SP.tile[i];
@@ -211,16 +244,22 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
     amp a[NR];
     uint32_t kpar = 0;  // parity of this group's full barrier
     uint32_t iter = 0;
+    uint32_t spar = 0;  // which of the two tile-part buffers this tile uses
+    auto slot_w = [&](const uint32_t sl) -> amp {
+        const uint8_t *const at = slot_area + (uint32_t)slot_ofs[sl] * 1024u;
+        if ((inv_mask >> sl) & 1u) return reinterpret_cast<const float2 *>(at)[tid];
+        return unit_phase((frac)(reinterpret_cast<const frac *>(at)[tid] + stile[spar + sl]), roots);
+    };
     for (uint32_t k = g;; k += 2u, ++iter) {
         const uint32_t t = blockIdx.x + k * gridDim.x;
         if (t >= ntiles) break;
         const uint64_t tbase = tile_base(t);
         uint64_t xloc = tbase | xthr0;
         // ---- tile part of the slotted phases: one thread per slot
-        const uint32_t spar = (iter & 1u) * QB2_MAX_SLOTS;
-        if (n_slots) {
+        spar = (iter & 1u) * QB2_MAX_SLOTS;
+        if (var_mask) {
             for (uint32_t sl = tid >> 5; sl < n_slots; sl += nthreads >> 5)
-                if ((tid & 31u) == 0u) {
+                if ((tid & 31u) == 0u && ((var_mask >> sl) & 1u)) {
                     const uint32_t so = slot_op[sl];
                     stile[spar + sl] = ladder_sum(ops[so & 0x7fffu], so >> 15, tbase);
                 }
@@ -228,7 +267,7 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
         bool tile_zero = false;
         if (zero_in) {
             tile_zero = sparse_synth<real, RB>(a, sp_tile, SP, t, tid);
-            if (n_slots) group_bar(g);
+            if (var_mask) group_bar(g);
         } else {
             mbar_wait(&full_bar[g], kpar);
             kpar ^= 1u;
@@ -254,25 +293,60 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
             if (tid == 0) tma_store_tile(&tmap, landing, (int)(tbase >> 4));
             continue;
         }
-        for (uint32_t p = 0; p < n_phases; ++p) {
-            const qb2_phase &ph = phases[p];
-            if (p > 0) {
-                // ---- exchange through the group's buffer
-                const uint2 c = ctx[p * nthreads + tid];
-                const uint32_t cz = (c.y & 0x1fffu) * (uint32_t)sizeof(vec), cw = ((c.y >> 13) & 0x1fffu) * (uint32_t)sizeof(vec);
-                const uint32_t xf = ph.xflags;
-                acquire_gbuf();
-                smem_store_any<RB, TMA_WIN>(gofs + cz, (xf & 1u) != 0u, xf >> 8 & 0xffu, a16 + ph.xw + TB, a);
-                group_bar(g);
-                {
-                    xloc = tbase | ctx_x(c);
-                    smem_load_any<RB, TMA_WIN>(gofs + cw, (xf & 2u) != 0u, xf >> 16 & 0xffu, a16 + ph.xr + TB, a);
-                }
-                group_bar(g);
+#define QB2_SLOT_W(sl) slot_w(sl)
+        if constexpr (JIT) {
+            // specialised kernel: phases and decode points are compile-time constants (jit_* tables of the
+            // generated translation unit), so every descriptor read folds and only the arms in use remain
+#define QB2_OP_DECL(name, idx) constexpr qb2_op name = jit_op(idx)
+#define QB2_PHASE_DECL(name, idx) constexpr qb2_phase name = jit_phase(idx)
+#define QB2_SWITCH(x) { constexpr uint32_t qb2_code_ = (x);
+#define QB2_CASE(c) if constexpr (qb2_code_ == (uint32_t)(c))
+#define QB2_BREAK
+#define QB2_DEFAULT
+#define QB2_SWITCH_END }
+#define QB2_ADVANCE(k)
+#define QB2_OPS_LOOP_BEGIN static_for<0, jit_ndec(p)>([&](auto Di) { constexpr uint32_t o = jit_sched(p, decltype(Di)::value);
+#define QB2_OPS_LOOP_END });
+            static_for<0, QB2_JIT_NPHASES>([&](auto Pc) {
+                constexpr uint32_t p = decltype(Pc)::value;
+#include "qb2_pass_tma_phase.inc"
+            });
+#undef QB2_OP_DECL
+#undef QB2_PHASE_DECL
+#undef QB2_SWITCH
+#undef QB2_CASE
+#undef QB2_BREAK
+#undef QB2_DEFAULT
+#undef QB2_SWITCH_END
+#undef QB2_OPS_LOOP_BEGIN
+#undef QB2_OPS_LOOP_END
+#undef QB2_ADVANCE
+        } else {
+#define QB2_OP_DECL(name, idx) const qb2_op &name = ops[idx]
+#define QB2_PHASE_DECL(name, idx) const qb2_phase &name = phases[idx]
+#define QB2_SWITCH(x) switch (x) {
+#define QB2_CASE(c) case (c):
+#define QB2_BREAK break;
+#define QB2_DEFAULT default: break;
+#define QB2_SWITCH_END }
+#define QB2_ADVANCE(k) o += (k)
+#define QB2_OPS_LOOP_BEGIN for (uint32_t o = ph.first_op, op_end = ph.first_op + ph.n_ops; o < op_end; ++o) {
+#define QB2_OPS_LOOP_END }
+            for (uint32_t p = 0; p < n_phases; ++p) {
+#include "qb2_pass_tma_phase.inc"
             }
-            const uint64_t X = hi_base | xloc;
-#include "qb2_pass_ops.inc"
+#undef QB2_OP_DECL
+#undef QB2_PHASE_DECL
+#undef QB2_SWITCH
+#undef QB2_CASE
+#undef QB2_BREAK
+#undef QB2_DEFAULT
+#undef QB2_SWITCH_END
+#undef QB2_OPS_LOOP_BEGIN
+#undef QB2_OPS_LOOP_END
+#undef QB2_ADVANCE
         }
+#undef QB2_SLOT_W
         // ---- the tile goes to the group's buffer in the layout of the tensor map, then ONE bulk store
         acquire_gbuf();
         {
@@ -285,6 +359,15 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
         if (tid == 0) tma_store_tile(&tmap, gbuf, (int)(tbase >> 4));
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(2 * TMA_GROUP, 1)
+    pass_kernel_tma(const __grid_constant__ CUtensorMap tmap, const uint32_t *__restrict__ tables, const uint64_t hi_base,
+                    const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off, const uint32_t sp_off,
+                    const uint32_t inv_mask, const uint32_t features, const SparseInput SP, const __grid_constant__ PassParams P) {
+    pass_tma_body<FULL, false>(tmap, tables, hi_base, ntiles, ctx_off, slot_off, sp_off, inv_mask, features, SP,
+                               reinterpret_cast<const uint8_t *>(&P));
 }
 
 typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -341,9 +424,42 @@ int launch_kernel_tma(const PassLaunch &L) {
     }
     const uint32_t ctx_off = NROOT * sizeof(float2) + 64u;
     const uint32_t slot_off = ctx_off + h->n_phases * TMA_GROUP * 8u;
-    const uint32_t slot_bytes = 4u * QB2_MAX_SLOTS * 4u + QB2_MAX_SLOTS * 2u + h->n_slots * TMA_GROUP * 4u;
-    const uint32_t sp_off = (slot_off + slot_bytes + 15u) & ~15u;
+    if (h->n_slots > QB2_MAX_SLOTS) return set_error(QB2_ELIMIT, "pass uses %u phase slots (at most %d)", h->n_slots, QB2_MAX_SLOTS);
+    // slots whose ladders read no bit outside the tile: their phase does not change from tile to tile, the kernel
+    // evaluates it once per CTA (2 KB of shared memory per such slot instead of 1 KB: as many as fit)
+    uint32_t inv_mask = 0;
+    {
+        const uint8_t *hb = reinterpret_cast<const uint8_t *>(h);
+        uint64_t nontile = 0;
+        for (int sgi = 0; sgi < h->n_seg; ++sgi) nontile |= ((1ull << h->seg[sgi].len) - 1ull) << h->seg[sgi].dst;
+        const qb2_op *ops = reinterpret_cast<const qb2_op *>(hb + h->ops_off);
+        const qb2_tab *tabs = reinterpret_cast<const qb2_tab *>(hb + h->tabdesc_off);
+        for (uint32_t o = 0; o < h->n_ops; ++o) {
+            const qb2_op &op = ops[o];
+            if (op.b1 == 0 || !(op.kind == QB2_OP_BFLY || op.kind == QB2_OP_DIAG_THR || op.kind == QB2_OP_DIAG_BIT)) continue;
+            const bool two = op.kind == QB2_OP_DIAG_BIT && !(op.flags & 1u);
+            const qb2_tab *tb = tabs + (op.kind == QB2_OP_BFLY ? (uint32_t)op.tab : (uint32_t)op.data);
+            for (uint32_t w = 0; w < (two ? 2u : 1u); ++w) {
+                const int cnt = (two && w == 0u) ? op.ntab_thr : op.ntab_thr + op.ntab_reg;
+                bool inv = true;
+                for (int i = 0; i < cnt && inv; ++i) {
+                    const qb2_mul &m = reinterpret_cast<const qb2_mul &>(tb[i]);
+                    if (!m.is_mul || (((uint64_t)m.mask << m.shift) & nontile) != 0ull) inv = false;
+                }
+                const uint32_t sl = op.b1 - 1u + w;
+                if (inv && sl < 32u) inv_mask |= 1u << sl;
+            }
+        }
+    }
+    static const bool no_inv = getenv("QB2_NO_SLOT_INV") != nullptr;  // (A/B switch for measurements)
+    if (no_inv) inv_mask = 0;
+    const uint32_t slot_fixed = 4u * QB2_MAX_SLOTS * 4u + 2u * QB2_MAX_SLOTS * 2u;
     const uint32_t sp_bytes = (h->features & QB2_FEATURE_ZERO_INPUT) ? ((L.sparse.count * 4u + 15u) & ~15u) : 0u;
+    auto slot_bytes_for = [&](uint32_t mask) { return slot_fixed + (h->n_slots + (uint32_t)__builtin_popcount(mask)) * TMA_GROUP * 4u; };
+    while (inv_mask && ((slot_off + slot_bytes_for(inv_mask) + 15u) & ~15u) + sp_bytes > TMA_AUX_BYTES)
+        inv_mask &= ~(1u << (31 - __builtin_clz(inv_mask)));  // drop the highest slot until the rest fits
+    const uint32_t slot_bytes = slot_bytes_for(inv_mask);
+    const uint32_t sp_off = (slot_off + slot_bytes + 15u) & ~15u;
     const uint32_t aux_bytes = sp_off + sp_bytes;
     if (aux_bytes > TMA_AUX_BYTES) return set_error(QB2_ELIMIT, "tma: descriptors need %u bytes of shared memory", aux_bytes);
     const size_t smem = (size_t)aux_bytes + 3u * TMA_TILE_BYTES;
@@ -361,7 +477,34 @@ int launch_kernel_tma(const PassLaunch &L) {
     PassParams params;
     memcpy(&params, h, h->small_bytes);
     const uint32_t *tables = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(L.blob_dev) + h->tab_off);
-    kern<<<grid, 2 * TMA_GROUP, smem, L.s>>>(tm, tables, L.hi_base, L.ntiles, ctx_off, slot_off, sp_off, L.sparse, params);
+    if (L.jit_kernel) {
+        // a kernel specialised for this pass's structure: same body, same arguments
+        uint64_t hi = L.hi_base;
+        uint32_t nt = L.ntiles, co = ctx_off, so = slot_off, spo = sp_off, im = inv_mask, ft = h->features;
+        SparseInput sp = L.sparse;
+        void *args[] = {&tm, &tables, &hi, &nt, &co, &so, &spo, &im, &ft, &sp, &params};
+        typedef CUresult (*attr_fn)(CUfunction, CUfunction_attribute, int);
+        typedef CUresult (*launch_fn)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+        static attr_fn set_attr = nullptr;
+        static launch_fn launch = nullptr;
+        if (!set_attr || !launch) {
+            cudaDriverEntryPointQueryResult q;
+            void *f1 = nullptr, *f2 = nullptr;
+            if (cudaGetDriverEntryPoint("cuFuncSetAttribute", &f1, cudaEnableDefault, &q) != cudaSuccess || !f1 ||
+                cudaGetDriverEntryPoint("cuLaunchKernel", &f2, cudaEnableDefault, &q) != cudaSuccess || !f2)
+                return set_error(QB2_ECUDA, "qb2_run_pass_jit: the driver has no cuLaunchKernel");
+            set_attr = reinterpret_cast<attr_fn>(f1);
+            launch = reinterpret_cast<launch_fn>(f2);
+        }
+        CUfunction fn = reinterpret_cast<CUfunction>(const_cast<void *>(L.jit_kernel));
+        CUresult r = set_attr(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 232448);
+        if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_run_pass_jit: cuFuncSetAttribute failed with %d", (int)r);
+        r = launch(fn, grid, 1, 1, 2 * TMA_GROUP, 1, 1, (unsigned)smem, (CUstream)L.s, args, nullptr);
+        if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_run_pass_jit: cuLaunchKernel failed with %d", (int)r);
+        count_launch();
+        return QB2_OK;
+    }
+    kern<<<grid, 2 * TMA_GROUP, smem, L.s>>>(tm, tables, L.hi_base, L.ntiles, ctx_off, slot_off, sp_off, inv_mask, h->features, L.sparse, params);
     count_launch();
     return check_cuda(cudaGetLastError(), "pass_kernel_tma launch");
 }

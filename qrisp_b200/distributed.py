@@ -57,9 +57,12 @@ def choose_evictions(pending, pos, n_local, g, protect):
 
 
 class ShardedStateVector(DeviceOps):
-    def __init__(self, num_qubits, group=None, dtype=np.complex64, device=None, T=None, r=None, L=4, tma=None, prefix_support=None):
+    def __init__(self, num_qubits, group=None, dtype=np.complex64, device=None, T=None, r=None, L=4, tma=None, prefix_support=None,
+                 specialize=None):
         import torch
         import torch.distributed as dist
+
+        self.specialize = (os.environ.get("QB2_SPECIALIZE", "0") not in ("", "0")) if specialize is None else bool(specialize)
 
         self.dist = dist
         self.group = group if group is not None else dist.group.WORLD

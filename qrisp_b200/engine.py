@@ -103,6 +103,21 @@ class DeviceOps:
             raw[56:60] = (int.from_bytes(raw[56:60], "little") | QB2_FEATURE_ZERO_INPUT).to_bytes(4, "little")
             header = ctypes.create_string_buffer(bytes(raw), len(raw))
             self._pending = None
+        kernel = getattr(step, "jit", None)
+        if kernel is None and getattr(self, "specialize", False) and getattr(step, "tma", False):
+            from . import jit
+
+            kernel = step.jit = jit.kernel_for(step)  # compiled once per pass structure (seconds), then cached
+        if kernel:
+            _lib.check(
+                self.lib.qb2_run_pass_jit(
+                    kernel, self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self._stream(),
+                    sp_ptr, sp_count,
+                ),
+                "qb2_run_pass_jit",
+            )
+            self.stats["jit_passes"] = self.stats.get("jit_passes", 0) + 1
+            return
         _lib.check(
             self.lib.qb2_run_pass(
                 self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream(),
@@ -207,8 +222,11 @@ class StateVector(DeviceOps):
     the reference's canonical order is ``pos[q] = num_qubits - 1 - q``.
     """
 
-    def __init__(self, num_qubits, dtype=np.complex64, device=None, T=None, r=None, L=4, tma=None, prefix_support=None):
+    def __init__(self, num_qubits, dtype=np.complex64, device=None, T=None, r=None, L=4, tma=None, prefix_support=None,
+                 specialize=None):
         torch = _torch()
+        # specialised pass kernels (qrisp_b200.jit): off unless asked for -- a first compilation costs seconds
+        self.specialize = (os.environ.get("QB2_SPECIALIZE", "0") not in ("", "0")) if specialize is None else bool(specialize)
         if not torch.cuda.is_available():
             raise _lib.Qb2Error("the B200 engine needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()
@@ -490,6 +508,18 @@ class Program:
         self.n_kernel_ops = sum(s.n_ops for s in steps if s.kind == "pass")
         self.n_gate_ops = sum(s.n_gate_ops for s in steps if s.kind == "pass") + sum(1 for s in steps if s.kind == "big")
         self.n_phases = sum(s.n_phases for s in steps if s.kind == "pass")
+
+    def specialize(self):
+        """Compile (or fetch from the cache) a specialised kernel for every TMA pass of this program
+        (:mod:`qrisp_b200.jit`); returns how many passes have one.  Replays then run without the interpreter."""
+        from . import jit
+
+        count = 0
+        for s in self.steps:
+            if s.kind == "pass" and getattr(s, "tma", False):
+                s.jit = jit.kernel_for(s)
+                count += 1 if s.jit else 0
+        return count
 
     def _enter(self):
         sv = self.sv

@@ -613,3 +613,42 @@ def test_dense_5q_blocks_on_the_tensor_cores(sim):
         assert simt.stats.get("block_tc", 0) == 0
         np.testing.assert_allclose(simt.statevector(), want, atol=ATOL64)
     print(f"tensor-core 5-qubit blocks: worst |amp - oracle| = {worst:.2e}")
+
+
+def test_specialised_pass_kernels_match_the_interpreter(sim):
+    """qrisp_b200.jit: a pass compiled with its structure as compile-time constants (same kernel source) gives
+    the interpreter's amplitudes -- and the oracle's -- on butterfly passes, random circuits and a sparse start;
+    a second program with the same structure but other angles reuses the kernel."""
+    from qrisp_b200 import jit
+    from qrisp_b200.engine import StateVector
+
+    if jit.find_nvcc() is None:
+        pytest.skip("no nvcc on this box: the interpreter stays in charge")
+    for qc, kw in ((ghz_qft_circuit(16), {}), (ghz_qft_circuit(17), {"prefix_support": 0}), (random_circuit(15, 4, seed=9), {})):
+        instrs = [i for i in qc.data if i.matrix is not None]
+        want = ref_sim.statevector(qc)
+        plain = StateVector(qc.num_qubits, **kw)
+        plain.apply_circuit(instrs)
+        fast = StateVector(qc.num_qubits, specialize=True, **kw)
+        fast.apply_circuit(instrs)
+        assert fast.stats.get("jit_passes", 0) >= 1 and plain.stats.get("jit_passes", 0) == 0, fast.stats
+        got = fast.statevector()
+        np.testing.assert_allclose(got, plain.statevector(), atol=2e-7)
+        np.testing.assert_allclose(got, want, atol=ATOL64)
+    # replayed program; same structure, other angles: one kernel
+    a, b = random_circuit(15, 3, seed=1), random_circuit(15, 3, seed=1)
+    for ins in b.data:
+        if ins.name == "u3" and ins.matrix is not None:
+            ins.matrix = ins.matrix @ np.diag([1, np.exp(0.3j)])
+    keys = []
+    for qc in (a, b):
+        sv = StateVector(15, specialize=True, prefix_support=0)
+        prog = sv.compile([i for i in qc.data if i.matrix is not None])
+        assert prog.specialize() >= 1
+        keys.append([jit.pass_key(jit.small_section(s.blob)) for s in prog.steps if s.kind == "pass" and s.tma])
+        sv.reset()
+        prog.run()
+        sv.reset()
+        prog.run()
+        np.testing.assert_allclose(sv.statevector(), ref_sim.statevector(qc), atol=ATOL64)
+    assert keys[0] == keys[1]
