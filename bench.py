@@ -468,8 +468,10 @@ def run_gpu_arm(args):
         sv.pos[:] = prog.pos_out
         per_pass_ms = [round(a.elapsed_time(b), 3) for a, b in pev]
     roofline = {
-        "kernel": "pass_kernel_tma<lean>: one cp.async.bulk.tensor load + store per 64 KB tile, 1 CTA x 2 groups x 256 threads per SM, "
-                  "32 amplitudes per thread, packed FP32x2 arithmetic" if all(getattr(s_, "tma", False) for s_ in prog.steps if s_.kind == "pass")
+        "kernel": ("qb2_pass_jit (pass_tma_body specialised per pass structure)" if jit_passes else "pass_kernel_tma<lean>")
+                  + ": one cp.async.bulk.tensor load + store per 64 KB tile, 1 CTA x 2 groups x 256 threads per SM, 32 amplitudes "
+                  "per thread, packed FP32x2 arithmetic; the first pass of a step = a streaming zero fill + the tiles that hold "
+                  "an entry of the sparse input" if all(getattr(s_, "tma", False) for s_ in prog.steps if s_.kind == "pass")
                   else "pass_kernel<float,RB=5,256,2> / pass_kernel_tma (mixed)",
         "bound": "hbm",
         "achieved": achieved,

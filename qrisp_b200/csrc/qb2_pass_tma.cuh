@@ -200,15 +200,37 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
         }
     }
     const uint32_t var_mask = (n_slots >= 32u ? 0xffffffffu : ((1u << n_slots) - 1u)) & ~inv_mask;  // slots with a tile part
-    // ---- sparse input (first pass after a reset): tile numbers of the listed amplitudes; the landing
-    // buffer is not needed for loads then and serves as the all-zero tile that empty tiles store
+    // ---- sparse input (first pass after a reset): the launcher has filled the whole shard with zeros (a
+    // plain streaming fill runs at 7.5 TB/s, tile-shaped bulk stores at 4.7); a tile without an entry stays
+    // zero under every op of the pass (the ops are linear), so the kernel only visits the tiles that have
+    // entries: the DISTINCT tile numbers of the (sorted) list, worked out here once per CTA.
     const bool zero_in = (features & QB2_FEATURE_ZERO_INPUT) != 0u;
     uint32_t *const sp_tile = reinterpret_cast<uint32_t *>(aux + sp_off);
+    uint32_t *const sp_uniq = sp_tile + ((SP.count + 3u) & ~3u);
+    uint32_t n_uniq = 0;
     if (zero_in) {
         for (uint32_t i = threadIdx.x; i < SP.count; i += blockDim.x) sp_tile[i] = SP.tile[i];
-        for (uint32_t i = threadIdx.x; i < TMA_TILE_BYTES / 16u; i += blockDim.x)
-            reinterpret_cast<uint4 *>(landing)[i] = make_uint4(0u, 0u, 0u, 0u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        // distinct tiles by warp ballots: chunk c = entries [32c, 32c+32); flag = first entry of its tile
+        uint32_t *const sp_cnt = sp_uniq + ((SP.count + 3u) & ~3u);  // [chunks] distinct tiles per chunk
+        const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const uint32_t chunks = (SP.count + 31u) >> 5;
+        for (uint32_t c = wid; c < chunks; c += nw) {
+            const uint32_t i = c * 32u + lane;
+            const bool first = i < SP.count && (i == 0u || sp_tile[i] != sp_tile[i - 1u]);
+            const uint32_t m = __ballot_sync(0xffffffffu, first);
+            if (lane == 0u) sp_cnt[c] = (uint32_t)__popc(m);
+        }
+        __syncthreads();
+        for (uint32_t c = wid; c < chunks; c += nw) {
+            uint32_t base = 0;
+            for (uint32_t d = 0; d < c; ++d) base += sp_cnt[d];
+            const uint32_t i = c * 32u + lane;
+            const bool first = i < SP.count && (i == 0u || sp_tile[i] != sp_tile[i - 1u]);
+            const uint32_t m = __ballot_sync(0xffffffffu, first);
+            if (first) sp_uniq[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = sp_tile[i];
+        }
+        for (uint32_t d = 0; d < chunks; ++d) n_uniq += sp_cnt[d];
     }
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
@@ -251,8 +273,13 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
         return unit_phase((frac)(reinterpret_cast<const frac *>(at)[tid] + stile[spar + sl]), roots);
     };
     for (uint32_t k = g;; k += 2u, ++iter) {
-        const uint32_t t = blockIdx.x + k * gridDim.x;
-        if (t >= ntiles) break;
+        uint32_t t = blockIdx.x + k * gridDim.x;
+        if (zero_in) {
+            if (t >= n_uniq) break;
+            t = sp_uniq[t];  // only tiles with an entry
+        } else if (t >= ntiles) {
+            break;
+        }
         const uint64_t tbase = tile_base(t);
         uint64_t xloc = tbase | xthr0;
         // ---- tile part of the slotted phases: one thread per slot
@@ -288,11 +315,7 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
                 gbuf_free = true;
             }
         };
-        if (tile_zero) {
-            // every op of the pass is linear: zeros stay zeros.  One bulk store of the zero tile.
-            if (tid == 0) tma_store_tile(&tmap, landing, (int)(tbase >> 4));
-            continue;
-        }
+        if (tile_zero) continue;  // (cannot happen: only listed tiles are visited)
 #define QB2_SLOT_W(sl) slot_w(sl)
         if constexpr (JIT) {
             // specialised kernel: phases and decode points are compile-time constants (jit_* tables of the
@@ -368,6 +391,31 @@ __global__ void __launch_bounds__(2 * TMA_GROUP, 1)
                     const uint32_t inv_mask, const uint32_t features, const SparseInput SP, const __grid_constant__ PassParams P) {
     pass_tma_body<FULL, false>(tmap, tables, hi_base, ntiles, ctx_off, slot_off, sp_off, inv_mask, features, SP,
                                reinterpret_cast<const uint8_t *>(&P));
+}
+
+// streaming fill of a shard with zeros: 16-byte stores, four per thread and iteration
+__global__ void __launch_bounds__(256) zero_fill_kernel(uint4 *__restrict__ p, const size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        __stcs(p + i, z);
+        __stcs(p + i + stride, z);
+        __stcs(p + i + 2 * stride, z);
+        __stcs(p + i + 3 * stride, z);
+    }
+    for (; i < n16; i += stride) __stcs(p + i, z);
+}
+
+inline int launch_zero_fill(void *state, size_t bytes, cudaStream_t s) {
+    const size_t n16 = bytes / 16;
+    size_t blocks = (n16 + 1023) / 1024;
+    const size_t cap = (size_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    zero_fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<uint4 *>(state), n16);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "zero_fill launch");
 }
 
 typedef CUresult (*tensor_map_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -454,7 +502,8 @@ int launch_kernel_tma(const PassLaunch &L) {
     static const bool no_inv = getenv("QB2_NO_SLOT_INV") != nullptr;  // (A/B switch for measurements)
     if (no_inv) inv_mask = 0;
     const uint32_t slot_fixed = 4u * QB2_MAX_SLOTS * 4u + 2u * QB2_MAX_SLOTS * 2u;
-    const uint32_t sp_bytes = (h->features & QB2_FEATURE_ZERO_INPUT) ? ((L.sparse.count * 4u + 15u) & ~15u) : 0u;
+    // sparse input: the tile numbers and the list of distinct ones
+    const uint32_t sp_bytes = (h->features & QB2_FEATURE_ZERO_INPUT) ? 2u * ((L.sparse.count * 4u + 15u) & ~15u) + 256u : 0u;
     auto slot_bytes_for = [&](uint32_t mask) { return slot_fixed + (h->n_slots + (uint32_t)__builtin_popcount(mask)) * TMA_GROUP * 4u; };
     while (inv_mask && ((slot_off + slot_bytes_for(inv_mask) + 15u) & ~15u) + sp_bytes > TMA_AUX_BYTES)
         inv_mask &= ~(1u << (31 - __builtin_clz(inv_mask)));  // drop the highest slot until the rest fits
@@ -474,6 +523,13 @@ int launch_kernel_tma(const PassLaunch &L) {
     }
     uint32_t grid = (uint32_t)sm_count();
     if (grid > L.ntiles) grid = L.ntiles;
+    if (h->features & QB2_FEATURE_ZERO_INPUT) {
+        // the state has not been written yet: zeros everywhere first (one streaming fill), then the pass visits
+        // the tiles that hold an entry of the sparse input
+        if (int rc = launch_zero_fill(L.state, (size_t)8 << h->n, L.s)) return rc;
+        if (L.sparse.count == 0) return QB2_OK;  // (a rank without entries: its shard is all zeros)
+        if (grid > L.sparse.count) grid = L.sparse.count;
+    }
     PassParams params;
     memcpy(&params, h, h->small_bytes);
     const uint32_t *tables = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(L.blob_dev) + h->tab_off);
