@@ -128,15 +128,16 @@ int qb2_apply_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, co
                          void *stream);
 
 /* Specialised pass kernels.  The host may compile, for ONE pass, a kernel whose descriptors are compile-time
- * constants (qrisp_b200/jit.py writes the translation unit -- the small section as a const array, the decode
- * schedule, then csrc/qb2_pass_tma.cuh -- and runs `nvcc -cubin -arch=sm_100a`): the interpreter's descriptor
- * reads, dispatch and address arithmetic fold away and only the arms in use remain.  qb2_jit_load maps such a
- * cubin (entry point `qb2_pass_jit`) and hands back the kernel; qb2_run_pass_jit is qb2_run_pass through it.
- * `header` / `blob_dev` MUST be the pass the kernel was built from (the caller keys its cache on the small
- * section); complex64 TMA passes only.  Results are those of qb2_run_pass. */
+ * constants (qrisp_b200/jit.py writes the translation unit -- phases, op records, decode schedule and slot maps
+ * as constexpr tables, then csrc/qb2_pass_tma.cuh or csrc/qb2_pass_kernel.cuh -- and runs `nvcc -cubin
+ * -arch=sm_100a`): the interpreter's dispatch, descriptor reads and address arithmetic fold away and only the
+ * arms in use remain; coefficients and tables are still read from the pass (same kernel for other angles).
+ * qb2_jit_load maps such a cubin (entry point `qb2_pass_jit`) and hands back the kernel; qb2_run_pass_jit is
+ * qb2_run_pass through it.  `header` / `blob_dev` MUST be a pass of the structure the kernel was built from (the
+ * caller keys its cache on it).  Results are those of qb2_run_pass. */
 int qb2_jit_load(const char *cubin_path, void **kernel_out);
 int qb2_run_pass_jit(void *kernel, void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev,
-                     void *stream, const void *sparse_dev, uint32_t n_sparse);
+                     int dtype, void *stream, const void *sparse_dev, uint32_t n_sparse);
 
 /* Dense 5-qubit block on the tensor cores (tcgen05.mma, TF32 x 3 split, accumulators in TMEM): the fast
  * path for the reference's grouped unitaries (circuit_preprocessing.py:119-157 `group_qc` ->

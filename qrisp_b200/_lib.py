@@ -45,7 +45,7 @@ SYMBOLS = {
     "qb2_jit_load": (_c.c_int, [_c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "qb2_run_pass_jit": (
         _c.c_int,
-        [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32],
+        [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32],
     ),
     "qb2_apply_matrix_big": (
         _c.c_int,

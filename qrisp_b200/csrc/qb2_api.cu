@@ -144,9 +144,10 @@ int qb2_jit_load(const char *cubin_path, void **kernel_out) {
 }
 
 int qb2_run_pass_jit(void *kernel, void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev,
-                     void *stream, const void *sparse_dev, uint32_t n_sparse) {
+                     int dtype, void *stream, const void *sparse_dev, uint32_t n_sparse) {
     if (!kernel) return set_error(QB2_EINVAL, "qb2_run_pass_jit: null kernel");
-    return launch_pass(state, n, hi_base, reinterpret_cast<const qb2_pass_header *>(header), blob_dev, QB2_C64,
+    if (int rc = check_dtype(dtype, "qb2_run_pass_jit")) return rc;
+    return launch_pass(state, n, hi_base, reinterpret_cast<const qb2_pass_header *>(header), blob_dev, dtype,
                        (cudaStream_t)stream, sparse_dev, n_sparse, kernel);
 }
 

@@ -111,8 +111,6 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
     L.sparse.amp = nullptr;
     L.sparse.count = 0;
     L.jit_kernel = jit_kernel;
-    if (jit_kernel && (!(h->features & QB2_FEATURE_TMA) || dtype != QB2_C64 || h->T != 13 || h->r != 5))
-        return set_error(QB2_EINVAL, "qb2_run_pass_jit: specialised kernels exist for TMA passes only");
     if (h->features & QB2_FEATURE_ZERO_INPUT) {
         if (n_sparse > QB2_MAX_SPARSE) return set_error(QB2_ELIMIT, "qb2_run_pass: %u sparse input entries (at most %d)", n_sparse, QB2_MAX_SPARSE);
         if (n_sparse && !sparse_dev) return set_error(QB2_EINVAL, "qb2_run_pass: sparse input list missing");

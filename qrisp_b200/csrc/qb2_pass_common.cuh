@@ -4,6 +4,8 @@
 // FFMA2 on the pair.  A complex multiplication is two instructions (the operand swizzles .LO_HI /
 // scalar splat / per-half negation are free), a real butterfly is two.
 #pragma once
+#include <cuda.h>  // CUfunction / CUtensorMap types; entry points come from cudaGetDriverEntryPoint
+
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -247,11 +249,22 @@ struct Gray {
     // bit that differs between Gray<G> and Gray<G+1>: the lowest zero bit of G
     static constexpr int flip = (G & 1) == 0 ? 0 : ((G & 2) == 0 ? 1 : ((G & 4) == 0 ? 2 : ((G & 8) == 0 ? 3 : ((G & 16) == 0 ? 4 : 5))));
 };
-template <int RB, int WIN>
-__device__ __forceinline__ void smem_store_gray(uint32_t off, const uint16_t *cols16, const float2 (&a)[1 << RB]) {
+// the columns of the register bits of one side of an exchange, as byte deltas (entry 1 << i of the slot
+// map's register part): read from the descriptors by the interpreter, constants in a specialised kernel
+template <int RB>
+struct GrayCols {
     uint32_t d[RB];
+};
+template <int RB>
+__device__ __forceinline__ GrayCols<RB> gray_cols(const uint16_t *cols16) {
+    GrayCols<RB> g;
 #pragma unroll
-    for (int i = 0; i < RB; ++i) d[i] = (uint32_t)cols16[1 << i] * (uint32_t)sizeof(float2);
+    for (int i = 0; i < RB; ++i) g.d[i] = (uint32_t)cols16[1 << i] * (uint32_t)sizeof(float2);
+    return g;
+}
+template <int RB, int WIN>
+__device__ __forceinline__ void smem_store_gray(uint32_t off, const GrayCols<RB> &gc, const float2 (&a)[1 << RB]) {
+    const uint32_t (&d)[RB] = gc.d;
     static_for<0, (1 << RB)>([&](auto Gi) {
         constexpr int g = decltype(Gi)::value;
         sts_amp<WIN>(off, a[Gray<g>::value]);
@@ -259,10 +272,8 @@ __device__ __forceinline__ void smem_store_gray(uint32_t off, const uint16_t *co
     });
 }
 template <int RB, int WIN>
-__device__ __forceinline__ void smem_load_gray(uint32_t off, const uint16_t *cols16, float2 (&a)[1 << RB]) {
-    uint32_t d[RB];
-#pragma unroll
-    for (int i = 0; i < RB; ++i) d[i] = (uint32_t)cols16[1 << i] * (uint32_t)sizeof(float2);
+__device__ __forceinline__ void smem_load_gray(uint32_t off, const GrayCols<RB> &gc, float2 (&a)[1 << RB]) {
+    const uint32_t (&d)[RB] = gc.d;
     static_for<0, (1 << RB)>([&](auto Gi) {
         constexpr int g = decltype(Gi)::value;
         a[Gray<g>::value] = lds_amp<WIN>(off);
@@ -286,7 +297,7 @@ __device__ __forceinline__ void smem_load_reg(const uint32_t off, float2 (&a)[1 
 }
 // one side of an exchange: `regular` = registers at base + (j << k) (k from the phase's xflags), else any map
 template <int RB, int WIN>
-__device__ __forceinline__ void smem_store_any(const uint32_t off, const bool regular, const uint32_t k, const uint16_t *cols16,
+__device__ __forceinline__ void smem_store_any(const uint32_t off, const bool regular, const uint32_t k, const GrayCols<RB> &cols16,
                                                const float2 (&a)[1 << RB]) {
     if (regular && k == 8u)
         smem_store_reg<RB, WIN, 8>(off, a);
@@ -298,7 +309,7 @@ __device__ __forceinline__ void smem_store_any(const uint32_t off, const bool re
         smem_store_gray<RB, WIN>(off, cols16, a);
 }
 template <int RB, int WIN>
-__device__ __forceinline__ void smem_load_any(const uint32_t off, const bool regular, const uint32_t k, const uint16_t *cols16,
+__device__ __forceinline__ void smem_load_any(const uint32_t off, const bool regular, const uint32_t k, const GrayCols<RB> &cols16,
                                               float2 (&a)[1 << RB]) {
     if (regular && k == 8u)
         smem_load_reg<RB, WIN, 8>(off, a);
@@ -325,6 +336,30 @@ __device__ unsigned long long qb2_trace_buf[QB2_TRACE_TILES * QB2_TRACE_STAMPS];
     do {      \
     } while (0)
 #endif
+
+// launch of a specialised kernel (a CUfunction from qb2_jit_load) through the driver entry points
+inline int launch_jit_kernel(const void *kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t s, void **args) {
+    typedef CUresult (*attr_fn)(CUfunction, CUfunction_attribute, int);
+    typedef CUresult (*launch_fn)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+    static attr_fn set_attr = nullptr;
+    static launch_fn launch = nullptr;
+    if (!set_attr || !launch) {
+        cudaDriverEntryPointQueryResult q;
+        void *f1 = nullptr, *f2 = nullptr;
+        if (cudaGetDriverEntryPoint("cuFuncSetAttribute", &f1, cudaEnableDefault, &q) != cudaSuccess || !f1 ||
+            cudaGetDriverEntryPoint("cuLaunchKernel", &f2, cudaEnableDefault, &q) != cudaSuccess || !f2)
+            return set_error(QB2_ECUDA, "qb2_run_pass_jit: the driver has no cuLaunchKernel");
+        set_attr = reinterpret_cast<attr_fn>(f1);
+        launch = reinterpret_cast<launch_fn>(f2);
+    }
+    CUfunction fn = reinterpret_cast<CUfunction>(const_cast<void *>(kernel));
+    CUresult r = set_attr(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem > 48 * 1024 ? (int)smem : 48 * 1024);
+    if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_run_pass_jit: cuFuncSetAttribute failed with %d", (int)r);
+    r = launch(fn, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)s, args, nullptr);
+    if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_run_pass_jit: cuLaunchKernel failed with %d", (int)r);
+    count_launch();
+    return QB2_OK;
+}
 
 struct PassParams {  // the small section of a pass, passed by value: lives in the constant bank
     uint4 q[QB2_MAX_SMALL_BYTES / 16];

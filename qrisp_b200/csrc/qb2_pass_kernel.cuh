@@ -19,6 +19,19 @@
 namespace qb2 {
 namespace {
 
+// The tables of a specialised kernel (generated translation unit: qrisp_b200/jit.py); dummies otherwise.
+#ifndef QB2_JIT_NPHASES
+#define QB2_JIT_NPHASES 1
+#define QB2_JIT_PHASES_FILE "qb2_jit_none.inc"
+#define QB2_JIT_TB 8
+__host__ __device__ constexpr uint32_t jit_ndec(uint32_t) { return 0; }
+__host__ __device__ constexpr uint32_t jit_sched(uint32_t, uint32_t) { return 0; }
+__host__ __device__ constexpr qb2_op jit_op(uint32_t) { return qb2_op{}; }
+__host__ __device__ constexpr qb2_phase jit_phase(uint32_t) { return qb2_phase{}; }
+__host__ __device__ constexpr uint32_t jit_a16(uint32_t) { return 0; }
+#define QB2_JIT_DUMMIES 1
+#endif
+
 // FULL = false leaves out the rarely used op kinds (general per-amplitude DIAG, 4x4 / 8x8 /
 // 16x16 blocks): the common passes then run a kernel a fraction of the size, which matters
 // because the interpreter's working set of code competes for the instruction cache.
@@ -29,11 +42,15 @@ namespace {
 // map (the irregular exchange path it forces costs what the gates cost); fetching the next tile into
 // the idle exchange buffer with cp.async during the last phase (issuing 32 eight-byte async copies
 // per thread costs more than the latency it hides: 25.9 vs 24.3 ms).
-template <typename real, int RB, int MAXT, int MINB, bool FULL>
-__global__ void __launch_bounds__(MAXT, MINB)
-    pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
-                const uint64_t hi_base, const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off,
-                const uint32_t tile_off, const SparseInput SP, const uint32_t sp_off, const __grid_constant__ PassParams P) {
+// (`pb`: the small section of the pass, the by-value kernel parameter; JIT: a specialised kernel whose phases, op
+// records, decode schedule and slot maps are compile-time constants of the generated translation unit, see
+// qb2_pass_tma.cuh and qrisp_b200/jit.py)
+template <typename real, int RB, bool FULL, bool JIT>
+__device__ __forceinline__ void pass_body(typename Traits<real>::vec *__restrict__ state,
+                                          const typename Traits<real>::frac *__restrict__ tables, const uint64_t hi_base,
+                                          const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off,
+                                          const uint32_t tile_off, const SparseInput &SP, const uint32_t sp_off,
+                                          const uint8_t *const pb) {
     using vec = typename Traits<real>::vec;
     using frac = typename Traits<real>::frac;
     using C = Cx<real>;
@@ -54,7 +71,6 @@ __global__ void __launch_bounds__(MAXT, MINB)
     }
 
     // every descriptor read below is a constant-bank load with a warp-uniform offset
-    const uint8_t *const pb = reinterpret_cast<const uint8_t *>(&P);
     const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(pb);
     const qb2_io *const IO = reinterpret_cast<const qb2_io *>(pb + QB2_IO_OFFSET);  // fixed offsets: immediate operands
     const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(pb + H->phases_off);
@@ -63,7 +79,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
     const uint16_t *const a16 = reinterpret_cast<const uint16_t *>(pb + H->u16_off);
     const uint64_t *const a64 = reinterpret_cast<const uint64_t *>(pb + H->u64_off);
     const qb2_tab *const tabs = reinterpret_cast<const qb2_tab *>(pb + H->tabdesc_off);
-    const int TB = (int)H->T - RB;  // thread bits
+    const int TB = JIT ? (int)QB2_JIT_TB : (int)H->T - RB;  // thread bits
     const uint32_t n_phases = H->n_phases;
     const int n_seg = H->n_seg;
 
@@ -202,74 +218,60 @@ __global__ void __launch_bounds__(MAXT, MINB)
             __syncthreads();
         }
         TR(2);
-        for (uint32_t p = 0; p < n_phases && !tile_zero; ++p) {
-            const qb2_phase &ph = phases[p];
-            if (p > 0) {
-                TR(4 + 2 * p);
-                // ---- exchange through shared memory
-                const uint4 c = ctx[p * nthreads + tid];
-                const uint32_t xf = ph.xflags;
-                {
-                    uint8_t *wp = tile_b + c.z;
-                    if (xf & 1u) {  // register j sits at slot j << kw: immediate offsets
-                        const uint32_t stride = (uint32_t)sizeof(vec) << (xf >> 8 & 0xffu);
-                        static_for<0, NR>([&](auto J) {
-                            constexpr int j = decltype(J)::value;
-                            *reinterpret_cast<amp *>(wp + j * stride) = a[j];
-                        });
-                    } else {
-                        const uint16_t *xw = a16 + ph.xw + TB;
-                        static_for<0, NR>([&](auto J) {
-                            constexpr int j = decltype(J)::value;
-                            *reinterpret_cast<amp *>(tile_b + (c.z ^ (xw[j] * (uint32_t)sizeof(vec)))) = a[j];
-                        });
-                    }
-                }
-                __syncthreads();
-                {
-                    xloc = tbase | ((uint64_t)c.y << 32 | c.x);
-                    const uint8_t *rp_ = tile_b + c.w;
-                    if (xf & 2u) {
-                        const uint32_t stride = (uint32_t)sizeof(vec) << (xf >> 16 & 0xffu);
-                        static_for<0, NR>([&](auto J) {
-                            constexpr int j = decltype(J)::value;
-                            a[j] = *reinterpret_cast<const amp *>(rp_ + j * stride);
-                        });
-                    } else {
-                        const uint16_t *xr = a16 + ph.xr + TB;
-                        static_for<0, NR>([&](auto J) {
-                            constexpr int j = decltype(J)::value;
-                            a[j] = *reinterpret_cast<const amp *>(tile_b + (c.w ^ (xr[j] * (uint32_t)sizeof(vec))));
-                        });
-                    }
-                }
-                __syncthreads();
-                TR(5 + 2 * p);
-            }
-            const uint64_t X = hi_base | xloc;
 #define QB2_SLOT_W(sl) unit_phase((frac)(sthr[(sl) * nthreads + tid] + stile[spar + (sl)]), roots)
-#define QB2_OP_DECL(name, idx) const qb2_op &name = ops[idx]
-#define QB2_PHASE_DECL(name, idx) const qb2_phase &name = phases[idx]
-#define QB2_SWITCH(x) switch (x) {
-#define QB2_CASE(c) case (c):
-#define QB2_BREAK break;
-#define QB2_DEFAULT default: break;
+        if constexpr (JIT) {
+#define QB2_OP_DECL(name, idx) constexpr qb2_op name = jit_op(idx)
+#define QB2_PHASE_DECL(name, idx) constexpr qb2_phase name = jit_phase(idx)
+#define QB2_A16(i) jit_a16(i)
+#define QB2_SWITCH(x) { constexpr uint32_t qb2_code_ = (x);
+#define QB2_CASE(c) if constexpr (qb2_code_ == (uint32_t)(c))
+#define QB2_BREAK
+#define QB2_DEFAULT
 #define QB2_SWITCH_END }
-#define QB2_ADVANCE(k) o += (k)
-            const uint32_t op_end = ph.first_op + ph.n_ops;
-            for (uint32_t o = ph.first_op; o < op_end; ++o) {
-#include "qb2_pass_ops.inc"
+#define QB2_ADVANCE(k)
+            if (!tile_zero) {
+#define QB2_PHASE_FILE "qb2_pass_kernel_phase.inc"
+#define QB2_DEP(x) ((x) + (JIT ? 0u : 0u))  /* value-dependent: the arms not taken are never instantiated */
+#include QB2_JIT_PHASES_FILE
+#undef QB2_DEP
+#undef QB2_PHASE_FILE
             }
 #undef QB2_OP_DECL
 #undef QB2_PHASE_DECL
+#undef QB2_A16
 #undef QB2_SWITCH
 #undef QB2_CASE
 #undef QB2_BREAK
 #undef QB2_DEFAULT
 #undef QB2_SWITCH_END
 #undef QB2_ADVANCE
-#undef QB2_SLOT_W
+#undef QB2_OPS_FILE
+        } else {
+#define QB2_OP_DECL(name, idx) const qb2_op &name = ops[idx]
+#define QB2_PHASE_DECL(name, idx) const qb2_phase &name = phases[idx]
+#define QB2_A16(i) a16[i]
+#define QB2_SWITCH(x) switch (x) {
+#define QB2_CASE(c) case (c):
+#define QB2_BREAK break;
+#define QB2_DEFAULT default: break;
+#define QB2_SWITCH_END }
+#define QB2_ADVANCE(k) o += (k)
+#define QB2_OPS_FILE "qb2_pass_ops_loop.inc"
+            for (uint32_t p = 0; p < n_phases && !tile_zero; ++p) {
+#include "qb2_pass_kernel_phase.inc"
+            }
+#undef QB2_OP_DECL
+#undef QB2_PHASE_DECL
+#undef QB2_A16
+#undef QB2_SWITCH
+#undef QB2_CASE
+#undef QB2_BREAK
+#undef QB2_DEFAULT
+#undef QB2_SWITCH_END
+#undef QB2_ADVANCE
+#undef QB2_OPS_FILE
         }
+#undef QB2_SLOT_W
         // ---- store with the last phase's distribution; load the next tile behind every store
         {
             TR(62);
@@ -305,6 +307,14 @@ __global__ void __launch_bounds__(MAXT, MINB)
     }
 }
 
+template <typename real, int RB, int MAXT, int MINB, bool FULL>
+__global__ void __launch_bounds__(MAXT, MINB)
+    pass_kernel(typename Traits<real>::vec *__restrict__ state, const typename Traits<real>::frac *__restrict__ tables,
+                const uint64_t hi_base, const uint32_t ntiles, const uint32_t ctx_off, const uint32_t slot_off,
+                const uint32_t tile_off, const SparseInput SP, const uint32_t sp_off, const __grid_constant__ PassParams P) {
+    pass_body<real, RB, FULL, false>(state, tables, hi_base, ntiles, ctx_off, slot_off, tile_off, SP, sp_off,
+                                     reinterpret_cast<const uint8_t *>(&P));
+}
 
 template <typename real, int RB, int MAXT, int MINB, bool FULL>
 int launch_kernel(const PassLaunch &L) {
@@ -351,6 +361,14 @@ int launch_kernel(const PassLaunch &L) {
     PassParams params;
     memcpy(&params, h, h->small_bytes);
     const frac *tables = reinterpret_cast<const frac *>(reinterpret_cast<const uint8_t *>(L.blob_dev) + h->tab_off);
+    if (L.jit_kernel) {
+        void *st = L.state;
+        uint64_t hi = L.hi_base;
+        uint32_t nt = L.ntiles, co = ctx_off, so = slot_off, to = tile_off, spo = sp_off;
+        SparseInput sp = L.sparse;
+        void *args[] = {&st, &tables, &hi, &nt, &co, &so, &to, &sp, &spo, &params};
+        return launch_jit_kernel(L.jit_kernel, grid, threads, smem, L.s, args);
+    }
     kern<<<grid, threads, smem, L.s>>>(reinterpret_cast<vec *>(L.state), tables, L.hi_base, L.ntiles, ctx_off, slot_off, tile_off,
                                        L.sparse, sp_off, params);
     count_launch();

@@ -66,11 +66,22 @@ __device__ __forceinline__ void group_bar(uint32_t g) { asm volatile("bar.sync %
 // The decode schedule of a specialised kernel (generated translation unit: qrisp_b200/jit.py); dummies here.
 #ifndef QB2_JIT_NPHASES
 #define QB2_JIT_NPHASES 1
+#define QB2_JIT_DUMMIES 1
+#define QB2_JIT_PHASES_FILE "qb2_jit_none.inc"
 __host__ __device__ constexpr uint32_t jit_ndec(uint32_t) { return 0; }
 __host__ __device__ constexpr uint32_t jit_sched(uint32_t, uint32_t) { return 0; }
 __host__ __device__ constexpr qb2_op jit_op(uint32_t) { return qb2_op{}; }
 __host__ __device__ constexpr qb2_phase jit_phase(uint32_t) { return qb2_phase{}; }
+__host__ __device__ constexpr uint32_t jit_a16(uint32_t) { return 0; }
 #endif
+
+template <int RB>
+__device__ __forceinline__ GrayCols<RB> jit_gray_cols(const uint32_t first) {
+    GrayCols<RB> g;
+#pragma unroll
+    for (int i = 0; i < RB; ++i) g.d[i] = jit_a16(first + (1u << i)) * (uint32_t)sizeof(float2);
+    return g;
+}
 
 // `pb`: the small section of the pass -- the by-value kernel parameter (constant bank) in the ahead-of-time
 // kernels, a const array with a known initialiser in a specialised one.  `features`: header.features as the
@@ -261,7 +272,19 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
     const uint64_t xthr0 = ctx_x(c0);
     const uint32_t land_rb = ((c0.y >> 13) & 0x1fffu) * (uint32_t)sizeof(vec);
     const uint32_t store_wb = (c0.y & 0x1fffu) * (uint32_t)sizeof(vec);
-    const uint32_t io_xf = phases[0].xflags;
+    // phase 0's maps = the landing buffer (load side) and the final store (store side)
+    uint32_t io_xf;
+    GrayCols<RB> io_rcols, io_wcols;
+    if constexpr (JIT) {
+        constexpr qb2_phase ph0 = jit_phase(0);
+        io_xf = ph0.xflags;
+        io_rcols = jit_gray_cols<RB>(ph0.xr + TB);
+        io_wcols = jit_gray_cols<RB>(ph0.xw + TB);
+    } else {
+        io_xf = phases[0].xflags;
+        io_rcols = gray_cols<RB>(a16 + phases[0].xr + TB);
+        io_wcols = gray_cols<RB>(a16 + phases[0].xw + TB);
+    }
 
     amp a[NR];
     uint32_t kpar = 0;  // parity of this group's full barrier
@@ -302,7 +325,7 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
             // addresses out of the tile loop and spilling them)
             uint32_t rb_t = land_rb;
             asm volatile("" : "+r"(rb_t));
-            smem_load_any<RB, TMA_WIN>(rb_t, (io_xf & 2u) != 0u, io_xf >> 16 & 0xffu, a16 + phases[0].xr + TB, a);
+            smem_load_any<RB, TMA_WIN>(rb_t, (io_xf & 2u) != 0u, io_xf >> 16 & 0xffu, io_rcols, a);
             group_bar(g);  // the landing buffer is free again (and the slots' tile parts are visible)
             if (tid == 0) issue_load(k + 1u);
         }
@@ -322,51 +345,52 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
             // generated translation unit), so every descriptor read folds and only the arms in use remain
 #define QB2_OP_DECL(name, idx) constexpr qb2_op name = jit_op(idx)
 #define QB2_PHASE_DECL(name, idx) constexpr qb2_phase name = jit_phase(idx)
+#define QB2_GRAY_COLS(first) jit_gray_cols<RB>(first)
 #define QB2_SWITCH(x) { constexpr uint32_t qb2_code_ = (x);
 #define QB2_CASE(c) if constexpr (qb2_code_ == (uint32_t)(c))
 #define QB2_BREAK
 #define QB2_DEFAULT
 #define QB2_SWITCH_END }
 #define QB2_ADVANCE(k)
-#define QB2_OPS_LOOP_BEGIN static_for<0, jit_ndec(p)>([&](auto Di) { constexpr uint32_t o = jit_sched(p, decltype(Di)::value);
-#define QB2_OPS_LOOP_END });
-            static_for<0, QB2_JIT_NPHASES>([&](auto Pc) {
-                constexpr uint32_t p = decltype(Pc)::value;
-#include "qb2_pass_tma_phase.inc"
-            });
+            // (textual unrolling, no lambdas around the phases: the registers must stay registers)
+#define QB2_PHASE_FILE "qb2_pass_tma_phase.inc"
+#define QB2_DEP(x) ((x) + (JIT ? 0u : 0u))  /* value-dependent: the arms not taken are never instantiated */
+#include QB2_JIT_PHASES_FILE
+#undef QB2_DEP
+#undef QB2_PHASE_FILE
 #undef QB2_OP_DECL
 #undef QB2_PHASE_DECL
+#undef QB2_GRAY_COLS
 #undef QB2_SWITCH
 #undef QB2_CASE
 #undef QB2_BREAK
 #undef QB2_DEFAULT
 #undef QB2_SWITCH_END
-#undef QB2_OPS_LOOP_BEGIN
-#undef QB2_OPS_LOOP_END
+#undef QB2_OPS_FILE
 #undef QB2_ADVANCE
         } else {
 #define QB2_OP_DECL(name, idx) const qb2_op &name = ops[idx]
 #define QB2_PHASE_DECL(name, idx) const qb2_phase &name = phases[idx]
+#define QB2_GRAY_COLS(first) gray_cols<RB>(a16 + (first))
 #define QB2_SWITCH(x) switch (x) {
 #define QB2_CASE(c) case (c):
 #define QB2_BREAK break;
 #define QB2_DEFAULT default: break;
 #define QB2_SWITCH_END }
 #define QB2_ADVANCE(k) o += (k)
-#define QB2_OPS_LOOP_BEGIN for (uint32_t o = ph.first_op, op_end = ph.first_op + ph.n_ops; o < op_end; ++o) {
-#define QB2_OPS_LOOP_END }
+#define QB2_OPS_FILE "qb2_pass_ops_loop.inc"
             for (uint32_t p = 0; p < n_phases; ++p) {
 #include "qb2_pass_tma_phase.inc"
             }
 #undef QB2_OP_DECL
 #undef QB2_PHASE_DECL
+#undef QB2_GRAY_COLS
 #undef QB2_SWITCH
 #undef QB2_CASE
 #undef QB2_BREAK
 #undef QB2_DEFAULT
 #undef QB2_SWITCH_END
-#undef QB2_OPS_LOOP_BEGIN
-#undef QB2_OPS_LOOP_END
+#undef QB2_OPS_FILE
 #undef QB2_ADVANCE
         }
 #undef QB2_SLOT_W
@@ -375,7 +399,7 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
         {
             uint32_t wb_t = gofs + store_wb;
             asm volatile("" : "+r"(wb_t));
-            smem_store_any<RB, TMA_WIN>(wb_t, (io_xf & 1u) != 0u, io_xf >> 8 & 0xffu, a16 + phases[0].xw + TB, a);
+            smem_store_any<RB, TMA_WIN>(wb_t, (io_xf & 1u) != 0u, io_xf >> 8 & 0xffu, io_wcols, a);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         group_bar(g);
@@ -539,26 +563,7 @@ int launch_kernel_tma(const PassLaunch &L) {
         uint32_t nt = L.ntiles, co = ctx_off, so = slot_off, spo = sp_off, im = inv_mask, ft = h->features;
         SparseInput sp = L.sparse;
         void *args[] = {&tm, &tables, &hi, &nt, &co, &so, &spo, &im, &ft, &sp, &params};
-        typedef CUresult (*attr_fn)(CUfunction, CUfunction_attribute, int);
-        typedef CUresult (*launch_fn)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
-        static attr_fn set_attr = nullptr;
-        static launch_fn launch = nullptr;
-        if (!set_attr || !launch) {
-            cudaDriverEntryPointQueryResult q;
-            void *f1 = nullptr, *f2 = nullptr;
-            if (cudaGetDriverEntryPoint("cuFuncSetAttribute", &f1, cudaEnableDefault, &q) != cudaSuccess || !f1 ||
-                cudaGetDriverEntryPoint("cuLaunchKernel", &f2, cudaEnableDefault, &q) != cudaSuccess || !f2)
-                return set_error(QB2_ECUDA, "qb2_run_pass_jit: the driver has no cuLaunchKernel");
-            set_attr = reinterpret_cast<attr_fn>(f1);
-            launch = reinterpret_cast<launch_fn>(f2);
-        }
-        CUfunction fn = reinterpret_cast<CUfunction>(const_cast<void *>(L.jit_kernel));
-        CUresult r = set_attr(fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, 232448);
-        if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_run_pass_jit: cuFuncSetAttribute failed with %d", (int)r);
-        r = launch(fn, grid, 1, 1, 2 * TMA_GROUP, 1, 1, (unsigned)smem, (CUstream)L.s, args, nullptr);
-        if (r != CUDA_SUCCESS) return set_error(QB2_ECUDA, "qb2_run_pass_jit: cuLaunchKernel failed with %d", (int)r);
-        count_launch();
-        return QB2_OK;
+        return launch_jit_kernel(L.jit_kernel, grid, 2 * TMA_GROUP, smem, L.s, args);
     }
     kern<<<grid, 2 * TMA_GROUP, smem, L.s>>>(tm, tables, L.hi_base, L.ntiles, ctx_off, slot_off, sp_off, inv_mask, h->features, L.sparse, params);
     count_launch();

@@ -104,15 +104,15 @@ class DeviceOps:
             header = ctypes.create_string_buffer(bytes(raw), len(raw))
             self._pending = None
         kernel = getattr(step, "jit", None)
-        if kernel is None and getattr(self, "specialize", False) and getattr(step, "tma", False):
+        if kernel is None and getattr(self, "specialize", False):
             from . import jit
 
             kernel = step.jit = jit.kernel_for(step)  # compiled once per pass structure (seconds), then cached
         if kernel:
             _lib.check(
                 self.lib.qb2_run_pass_jit(
-                    kernel, self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self._stream(),
-                    sp_ptr, sp_count,
+                    kernel, self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype,
+                    self._stream(), sp_ptr, sp_count,
                 ),
                 "qb2_run_pass_jit",
             )
@@ -514,12 +514,10 @@ class Program:
         (:mod:`qrisp_b200.jit`); returns how many passes have one.  Replays then run without the interpreter."""
         from . import jit
 
-        count = 0
-        for s in self.steps:
-            if s.kind == "pass" and getattr(s, "tma", False):
-                s.jit = jit.kernel_for(s)
-                count += 1 if s.jit else 0
-        return count
+        passes = [s for s in self.steps if s.kind == "pass"]
+        for s, k in zip(passes, jit.kernels_for(passes)):
+            s.jit = k
+        return sum(1 for s in passes if s.jit)
 
     def _enter(self):
         sv = self.sv

@@ -645,7 +645,7 @@ def test_specialised_pass_kernels_match_the_interpreter(sim):
         sv = StateVector(15, specialize=True, prefix_support=0)
         prog = sv.compile([i for i in qc.data if i.matrix is not None])
         assert prog.specialize() >= 1
-        keys.append([jit.pass_key(jit.small_section(s.blob)) for s in prog.steps if s.kind == "pass" and s.tma])
+        keys.append([jit.pass_key(jit.small_section(s.blob), s.tma) for s in prog.steps if s.kind == "pass"])
         sv.reset()
         prog.run()
         sv.reset()
