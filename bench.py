@@ -74,11 +74,16 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi needs a moment before its first line: wait for it (the run itself is over in a fraction of
+            # a second once the kernels are cached)
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.02)
         except OSError:
             self.proc = None
 
@@ -234,19 +239,19 @@ def cpu_threads():
         return HOST_CORES
 
 
-def sample_width_for(steps, budget_s, n_max):
+def sample_width_for(steps, budget_s, n_max, with_run=True):
     """Width of the per-step CPU sample, MEASURED: a probe at 18 and 20 qubits gives this box's time per
     step and its growth per qubit (about 2x); the widest register whose predicted `steps` steps fit into
     `budget_s` is taken (the QB2_CPU_SAMPLE_QUBITS environment variable caps it)."""
-    cap = min(n_max, env_int("QB2_CPU_SAMPLE_QUBITS", 27))
+    cap = min(n_max, env_int("QB2_CPU_SAMPLE_QUBITS", 25))  # (the reference's run() leg grows faster than 2x per qubit beyond 25)
     cpu_sample(12)  # warm-up: imports, numba compilation, thread pools
     if cap <= 18:
         return cap
-    t18 = cpu_sample(18)
-    t20 = cpu_sample(20)
+    t18 = cpu_sample(18, with_run)
+    t20 = cpu_sample(20, with_run)
     per18 = t18["sim_s"] + (t18["run_s"] or 0.0)
     per20 = t20["sim_s"] + (t20["run_s"] or 0.0)
-    growth = min(2.3, max(1.8, (per20 / max(per18, 1e-6)) ** 0.5))  # per qubit; the dense regime doubles
+    growth = min(3.0, max(2.0, (per20 / max(per18, 1e-6)) ** 0.5))  # per qubit; the dense regime at least doubles
     n, t = 20, per20
     while n < cap and steps * t * growth <= budget_s:
         n += 1
@@ -358,11 +363,11 @@ def run_gpu_arm(args):
     if world == 1:
         from qrisp_b200.engine import StateVector
 
-        sv = StateVector(n_total)
+        sv = StateVector(n_total, specialize=False if args.no_specialize else None)
     else:
         from qrisp_b200.distributed import ShardedStateVector
 
-        sv = ShardedStateVector(n_total, group=dist.group.WORLD)
+        sv = ShardedStateVector(n_total, group=dist.group.WORLD, specialize=False if args.no_specialize else None)
 
     def barrier():
         if dist is not None:
@@ -547,8 +552,8 @@ def run_gpu_arm(args):
     # ---- CPU baseline on this box's host cores (bounded sample)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        width = sample_width_for(1, CPU_BASELINE_BUDGET_S, n_total)
-        info = cpu_sample(width)
+        width = sample_width_for(1, CPU_BASELINE_BUDGET_S, n_total, with_run=False)
+        info = cpu_sample(width, with_run=False)
         cpu_baseline = {
             "value": info["n_gates"] * float(1 << width) / info["sim_s"],
             "unit": UNIT,

@@ -62,7 +62,9 @@ class ShardedStateVector(DeviceOps):
         import torch
         import torch.distributed as dist
 
-        self.specialize = (os.environ.get("QB2_SPECIALIZE", "0") not in ("", "0")) if specialize is None else bool(specialize)
+        from .engine import _specialize_mode
+
+        self.specialize = _specialize_mode(specialize)
 
         self.dist = dist
         self.group = group if group is not None else dist.group.WORLD

@@ -29,6 +29,15 @@ def _torch():
     return torch
 
 
+def _specialize_mode(arg):
+    if arg is not None:
+        return bool(arg)
+    env = os.environ.get("QB2_SPECIALIZE")
+    if env is None or env == "":
+        return None
+    return env != "0"
+
+
 class DeviceOps:
     """How a state object talks to libqb2.so; shared by the single-device and the sharded
     state.  (CPU tests of the sharding logic substitute these four methods.)"""
@@ -104,10 +113,13 @@ class DeviceOps:
             header = ctypes.create_string_buffer(bytes(raw), len(raw))
             self._pending = None
         kernel = getattr(step, "jit", None)
-        if kernel is None and getattr(self, "specialize", False):
+        mode = getattr(self, "specialize", False)
+        if kernel is None and mode is not False and not hasattr(step, "jit"):
             from . import jit
 
-            kernel = step.jit = jit.kernel_for(step)  # compiled once per pass structure (seconds), then cached
+            # True: compiled once per pass structure (seconds), then cached; None (the default): only what the
+            # cache already holds -- a kernel somebody has paid for is used, nothing is ever compiled unasked
+            kernel = step.jit = jit.kernel_for(step, build=mode is True)
         if kernel:
             _lib.check(
                 self.lib.qb2_run_pass_jit(
@@ -225,8 +237,9 @@ class StateVector(DeviceOps):
     def __init__(self, num_qubits, dtype=np.complex64, device=None, T=None, r=None, L=4, tma=None, prefix_support=None,
                  specialize=None):
         torch = _torch()
-        # specialised pass kernels (qrisp_b200.jit): off unless asked for -- a first compilation costs seconds
-        self.specialize = (os.environ.get("QB2_SPECIALIZE", "0") not in ("", "0")) if specialize is None else bool(specialize)
+        # specialised pass kernels (qrisp_b200.jit).  True: compile what is missing (seconds per pass, once);
+        # False: interpreter only; None (default): use kernels that are already in the cache, compile nothing
+        self.specialize = _specialize_mode(specialize)
         if not torch.cuda.is_available():
             raise _lib.Qb2Error("the B200 engine needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()

@@ -11,10 +11,11 @@ is left is straight-line arithmetic plus the tile movement.  Results are those o
 same arithmetic).
 
 Cubins are cached by the SHA-256 of (small section, kernel sources) under ``qrisp_b200/jit_cache/`` (override:
-``QB2_JIT_CACHE``) and loaded through ``qb2_jit_load``.  Specialisation is opt-in
-(``StateVector(..., specialize=True)`` / ``QB2_SPECIALIZE=1`` / ``Program.specialize()``): a first compilation
-costs seconds per pass, which only a replayed program earns back.  Without ``nvcc`` the interpreter simply
-stays in charge.  Both pass kernels (TMA and register-pipelined), every geometry.
+``QB2_JIT_CACHE``) and loaded through ``qb2_jit_load``.  Compilation is opt-in
+(``StateVector(..., specialize=True)`` / ``QB2_SPECIALIZE=1`` / ``Program.specialize()``): it costs seconds per
+pass, which only a replayed program earns back.  By default an engine uses the kernels the cache already holds
+and compiles nothing (``specialize=False`` / ``QB2_SPECIALIZE=0``: interpreter only).  Without ``nvcc`` the
+interpreter simply stays in charge.  Both pass kernels (TMA and register-pipelined), every geometry.
 """
 
 from __future__ import annotations

@@ -627,7 +627,7 @@ def test_specialised_pass_kernels_match_the_interpreter(sim):
     for qc, kw in ((ghz_qft_circuit(16), {}), (ghz_qft_circuit(17), {"prefix_support": 0}), (random_circuit(15, 4, seed=9), {})):
         instrs = [i for i in qc.data if i.matrix is not None]
         want = ref_sim.statevector(qc)
-        plain = StateVector(qc.num_qubits, **kw)
+        plain = StateVector(qc.num_qubits, specialize=False, **kw)
         plain.apply_circuit(instrs)
         fast = StateVector(qc.num_qubits, specialize=True, **kw)
         fast.apply_circuit(instrs)

@@ -16,7 +16,7 @@ instrs = [i for i in qc.data if i.matrix is not None]
 out = {"circuit": kind, "qubits": n, "gates": len(instrs)}
 ref = None
 for label in ("interpreter", "specialised"):
-    sv = StateVector(n)
+    sv = StateVector(n, specialize=False)
     prog = sv.compile(instrs)
     if label == "specialised":
         t0 = time.perf_counter()
