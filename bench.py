@@ -240,22 +240,19 @@ def cpu_threads():
 
 
 def sample_width_for(steps, budget_s, n_max, with_run=True):
-    """Width of the per-step CPU sample, MEASURED: a probe at 18 and 20 qubits gives this box's time per
-    step and its growth per qubit (about 2x); the widest register whose predicted `steps` steps fit into
-    `budget_s` is taken (the QB2_CPU_SAMPLE_QUBITS environment variable caps it)."""
-    cap = min(n_max, env_int("QB2_CPU_SAMPLE_QUBITS", 25))  # (the reference's run() leg grows faster than 2x per qubit beyond 25)
-    cpu_sample(12)  # warm-up: imports, numba compilation, thread pools
-    if cap <= 18:
+    """Width of the per-step CPU sample, MEASURED: a probe at 20 qubits gives this box's time per step; the
+    dense regime costs a good factor 2 per further qubit (2.2 is used), and the widest register whose predicted
+    `steps` steps fit into `budget_s` is taken, 25 qubits at most (QB2_CPU_SAMPLE_QUBITS lowers the cap)."""
+    cap = min(n_max, env_int("QB2_CPU_SAMPLE_QUBITS", 25))
+    cpu_sample(12, with_run)  # warm-up: imports, numba compilation, thread pools
+    if cap <= 20:
         return cap
-    t18 = cpu_sample(18, with_run)
-    t20 = cpu_sample(20, with_run)
-    per18 = t18["sim_s"] + (t18["run_s"] or 0.0)
-    per20 = t20["sim_s"] + (t20["run_s"] or 0.0)
-    growth = min(3.0, max(2.0, (per20 / max(per18, 1e-6)) ** 0.5))  # per qubit; the dense regime at least doubles
-    n, t = 20, per20
-    while n < cap and steps * t * growth <= budget_s:
+    cpu_sample(16, with_run)
+    probe = cpu_sample(20, with_run)
+    n, t = 20, probe["sim_s"] + (probe["run_s"] or 0.0)
+    while n < cap and steps * t * 2.2 <= budget_s:
         n += 1
-        t *= growth
+        t *= 2.2
     return n
 
 
@@ -391,7 +388,11 @@ def run_gpu_arm(args):
     jit_passes = 0
     if not args.no_specialize:
         t_jit = time.perf_counter()
+        if dist is not None and rank != 0:
+            dist.barrier()  # rank 0 compiles, the others find the cubins in the cache
         jit_passes = prog.specialize()
+        if dist is not None and rank == 0:
+            dist.barrier()
         t_jit = time.perf_counter() - t_jit
 
     def step():

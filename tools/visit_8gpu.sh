@@ -10,7 +10,8 @@ for N in 4 8; do
   timeout 300 $TR --nproc-per-node $N --master-port 2951$N bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${TAG}_${N}gpu.json 2> gpurun_out/bench_${TAG}_${N}gpu.err; echo "bench$N rc=$?"; cut -c1-700 gpurun_out/bench_${TAG}_${N}gpu.json
 done
 : > gpurun_out/dist_${TAG}_8gpu.jsonl
+export QB2_SPECIALIZE=1
 for ARGS in "qft 36" "random 22 20" "random 33 20" "random 36 20" "qft 33"; do
-  timeout 400 $TR --nproc-per-node 8 --master-port 29530 tools/run_circuit_dist.py $ARGS 2> gpurun_out/dist_${TAG}_8gpu.err | grep '^{' | tee -a gpurun_out/dist_${TAG}_8gpu.jsonl; echo "$ARGS rc=${PIPESTATUS[0]}"
+  timeout 600 $TR --nproc-per-node 8 --master-port 29530 tools/run_circuit_dist.py $ARGS 2> gpurun_out/dist_${TAG}_8gpu.err | grep '^{' | tee -a gpurun_out/dist_${TAG}_8gpu.jsonl; echo "$ARGS rc=${PIPESTATUS[0]}"
 done
 tail -5 gpurun_out/dist_${TAG}_8gpu.err
