@@ -635,6 +635,12 @@ def test_specialised_pass_kernels_match_the_interpreter(sim):
         got = fast.statevector()
         np.testing.assert_allclose(got, plain.statevector(), atol=2e-7)
         np.testing.assert_allclose(got, want, atol=ATOL64)
+    # complex128: the register-pipelined kernel's other geometry
+    qc = random_circuit(13, 3, seed=5, two_qubit="cx")
+    fast = StateVector(13, dtype=np.complex128, specialize=True)
+    fast.apply_circuit([i for i in qc.data if i.matrix is not None])
+    assert fast.stats.get("jit_passes", 0) >= 1
+    np.testing.assert_allclose(fast.statevector(), ref_sim.statevector(qc, dtype=np.complex128), atol=ATOL128)
     # replayed program; same structure, other angles: one kernel
     a, b = random_circuit(15, 3, seed=1), random_circuit(15, 3, seed=1)
     for ins in b.data:
