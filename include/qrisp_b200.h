@@ -152,6 +152,16 @@ int qb2_apply_block_tc(void *state, int n, uint64_t hi_base, const void *block_d
  * 64 x 64 operand in the kernel's shared-memory layout (QB2_BLOCK_TC_BYTES bytes at `out_host`). */
 int qb2_pack_block_tc(const void *matrix_c128_host, void *out_host);
 
+/* Multiplexed real rotation (the middle factor of a cosine-sine decomposition): on position `target` the
+ * rotation [[c_j, -s_j], [s_j, c_j]], j spelled by the `n_ctrl` positions `ctrl[]` (bit i of j = position ctrl[i];
+ * positions >= n read `hi_base`); `cs_dev`: DEVICE array of 2**n_ctrl (cos, sin) pairs in the state's real type.
+ * Further controls over the physical index as in a pass.  In place, one sweep.  With it the host applies a dense
+ * block on 6..8 qubits (reference: tensor_factor.py:67-89 on a `group_qc` unitary) as controlled 5-qubit blocks on
+ * the tensor cores plus k - 5 of these sweeps. */
+#define QB2_MUX_MAX_CONTROLS 7
+int qb2_apply_mux_ry(void *state, int n, uint64_t hi_base, int target, const int *ctrl, int n_ctrl, const void *cs_dev,
+                     uint64_t ctrl_mask, uint64_t ctrl_value, int dtype, void *stream);
+
 /* ---------------------------------------------------------------- layout
  * dst[j] = src[i] where bit perm[p] of j = bit p of i (out of place).  Used to return a
  * statevector in the reference's canonical order (simulator.py:288 `qs.eval()`), and for

@@ -57,6 +57,11 @@ SYMBOLS = {
         [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.POINTER(_c.c_int), _c.c_uint64, _c.c_uint64, _c.c_void_p],
     ),
     "qb2_pack_block_tc": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "qb2_apply_mux_ry": (
+        _c.c_int,
+        [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_int, _c.POINTER(_c.c_int), _c.c_int, _c.c_void_p, _c.c_uint64, _c.c_uint64,
+         _c.c_int, _c.c_void_p],
+    ),
     "qb2_swap_pull": (
         _c.c_int,
         [_c.c_void_p, _c.POINTER(_c.c_void_p), _c.c_int, _c.c_int, _c.c_int, _c.POINTER(_c.c_int), _c.c_int, _c.c_void_p],

@@ -165,6 +165,12 @@ int qb2_apply_block_tc(void *state, int n, uint64_t hi_base, const void *block_d
     return launch_block_tc(state, n, hi_base, block_dev, targets, ctrl_mask, ctrl_value, (cudaStream_t)stream);
 }
 
+int qb2_apply_mux_ry(void *state, int n, uint64_t hi_base, int target, const int *ctrl, int n_ctrl, const void *cs_dev,
+                     uint64_t ctrl_mask, uint64_t ctrl_value, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_apply_mux_ry")) return rc;
+    return launch_mux_ry(state, n, hi_base, target, ctrl, n_ctrl, cs_dev, ctrl_mask, ctrl_value, dtype, (cudaStream_t)stream);
+}
+
 int qb2_pack_block_tc(const void *matrix_c128_host, void *out_host) {
     if (!matrix_c128_host || !out_host) return set_error(QB2_EINVAL, "qb2_pack_block_tc: null pointer");
     return pack_block_tc(reinterpret_cast<const double *>(matrix_c128_host), reinterpret_cast<float *>(out_host));

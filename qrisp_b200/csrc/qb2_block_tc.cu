@@ -244,6 +244,80 @@ int launch_block_tc(void *state, int n, uint64_t hi_base, const void *gate_dev, 
     return check_cuda(cudaGetLastError(), "block5_tc_kernel launch");
 }
 
+// ---------------------------------------------------------------- multiplexed real rotation
+// The middle factor of a cosine-sine decomposition: on `target`, the rotation [[c_j, -s_j], [s_j, c_j]] where j
+// is spelled by the `nc` control positions (a uniformly controlled Ry).  Streaming, HBM bound: 16 B per
+// amplitude.  With it a dense block on k = 6..8 qubits becomes controlled 5-qubit blocks on the tensor cores
+// and k - 5 of these sweeps (engine.py: _run_block_csd).
+namespace {
+
+struct MuxDesc {
+    int target;
+    int nc;
+    int ctrl[QB2_MUX_MAX_CONTROLS];
+};
+
+template <typename vec, typename real>
+__global__ void __launch_bounds__(256) mux_ry_kernel(vec *__restrict__ state, const uint64_t pairs, const uint64_t hi_base,
+                                                     const MuxDesc D, const vec *__restrict__ cs, const uint64_t cmask,
+                                                     const uint64_t cval) {
+    extern __shared__ __align__(16) uint8_t mux_smem[];
+    vec *const tab = reinterpret_cast<vec *>(mux_smem);
+    for (uint32_t i = threadIdx.x; i < (1u << D.nc); i += blockDim.x) tab[i] = cs[i];
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t tbit = 1ull << D.target;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < pairs; p += stride) {
+        const uint64_t i0 = ((p >> D.target) << (D.target + 1)) | (p & (tbit - 1ull));
+        const uint64_t x = i0 | hi_base;
+        if (((x ^ cval) & cmask) != 0ull) continue;
+        uint32_t j = 0;
+#pragma unroll
+        for (int c = 0; c < QB2_MUX_MAX_CONTROLS; ++c)
+            if (c < D.nc) j |= (uint32_t)((x >> D.ctrl[c]) & 1ull) << c;
+        const vec w = tab[j];  // (cos, sin)
+        const vec a0 = state[i0], a1 = state[i0 | tbit];
+        vec b0, b1;
+        b0.x = w.x * a0.x - w.y * a1.x;
+        b0.y = w.x * a0.y - w.y * a1.y;
+        b1.x = w.y * a0.x + w.x * a1.x;
+        b1.y = w.y * a0.y + w.x * a1.y;
+        state[i0] = b0;
+        state[i0 | tbit] = b1;
+    }
+}
+
+}  // namespace
+
+int launch_mux_ry(void *state, int n, uint64_t hi_base, int target, const int *ctrl, int nc, const void *cs_dev, uint64_t cmask,
+                  uint64_t cval, int dtype, cudaStream_t s) {
+    if (!state || !cs_dev || n < 1 || n > 40 || target < 0 || target >= n || nc < 0 || nc > QB2_MUX_MAX_CONTROLS || (nc && !ctrl))
+        return set_error(QB2_EINVAL, "qb2_apply_mux_ry: bad arguments");
+    MuxDesc D;
+    D.target = target;
+    D.nc = nc;
+    for (int c = 0; c < QB2_MUX_MAX_CONTROLS; ++c) D.ctrl[c] = 0;
+    for (int c = 0; c < nc; ++c) {
+        if (ctrl[c] < 0 || ctrl[c] >= 64 || ctrl[c] == target) return set_error(QB2_EINVAL, "qb2_apply_mux_ry: bad control position");
+        D.ctrl[c] = ctrl[c];
+    }
+    if ((cmask >> target) & 1ull) return set_error(QB2_EINVAL, "qb2_apply_mux_ry: the target is also a control");
+    const uint64_t pairs = 1ull << (n - 1);
+    uint64_t blocks = (pairs + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == QB2_C64)
+        mux_ry_kernel<float2, float><<<(unsigned)blocks, 256, sizeof(float2) << nc, s>>>(reinterpret_cast<float2 *>(state), pairs, hi_base, D,
+                                                                                   reinterpret_cast<const float2 *>(cs_dev), cmask, cval);
+    else if (dtype == QB2_C128)
+        mux_ry_kernel<double2, double><<<(unsigned)blocks, 256, sizeof(double2) << nc, s>>>(reinterpret_cast<double2 *>(state), pairs, hi_base, D,
+                                                                                      reinterpret_cast<const double2 *>(cs_dev), cmask, cval);
+    else
+        return set_error(QB2_EINVAL, "qb2_apply_mux_ry: bad dtype %d", dtype);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "mux_ry launch");
+}
+
 // host: U (32 x 32 complex128, row-major, index bit i <-> targets[i]) -> B_hi, B_lo in the kernel's layout
 int pack_block_tc(const double *u, float *out) {
     float *hi = out, *lo = out + TC_R * TC_R;

@@ -81,6 +81,8 @@ int launch_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, const
 int launch_block_tc(void *state, int n, uint64_t hi_base, const void *gate_dev, const int *targets, uint64_t cmask, uint64_t cval,
                     cudaStream_t s);
 int pack_block_tc(const double *u, float *out);
+int launch_mux_ry(void *state, int n, uint64_t hi_base, int target, const int *ctrl, int nc, const void *cs_dev, uint64_t cmask,
+                  uint64_t cval, int dtype, cudaStream_t s);
 int launch_swap_pull(void *dst, const void *const *peers, int world, int rank, int n, const int *perm, int dtype, cudaStream_t s);
 int launch_permute_bits(const void *src, void *dst, int n, const int *perm, int dtype, cudaStream_t s);
 int launch_norm2(const void *state, int n, double *out_dev, int dtype, cudaStream_t s);

@@ -204,10 +204,58 @@ class DeviceOps:
         self.stats["big"] += 1
         self.stats["block_tc"] = self.stats.get("block_tc", 0) + 1
 
+    def _csd_steps(self, matrix, positions, cmask, cval, out):
+        """Cosine-sine decomposition down to 5-qubit blocks.  ``matrix``: index bit i <-> positions[i].  Appends
+        ("tc", positions, matrix, cmask, cval) and ("mux", target, controls, theta, cmask, cval) in the order they
+        act on the state:  U = diag(u1, u2) . CS(theta) . diag(v1h, v2h), split on the top index bit."""
+        k = len(positions)
+        if k == 5:
+            out.append(("tc", list(positions), matrix, cmask, cval))
+            return
+        from scipy.linalg import cossin
+
+        half = 1 << (k - 1)
+        (u1, u2), theta, (v1h, v2h) = cossin(np.asarray(matrix, dtype=np.complex128), p=half, q=half, separate=True)
+        top, rest = int(positions[k - 1]), list(positions[: k - 1])
+        bit = 1 << top
+        self._csd_steps(v1h, rest, cmask | bit, cval, out)
+        self._csd_steps(v2h, rest, cmask | bit, cval | bit, out)
+        out.append(("mux", top, rest, np.asarray(theta, dtype=np.float64), cmask, cval))
+        self._csd_steps(u1, rest, cmask | bit, cval, out)
+        self._csd_steps(u2, rest, cmask | bit, cval | bit, out)
+
+    def _run_block_csd(self, s):
+        """A dense block on 6..8 qubits: controlled 5-qubit blocks on the tensor cores around multiplexed real
+        rotations (qb2_apply_mux_ry), from the cosine-sine decomposition of the matrix (host, scipy)."""
+        from .planner import BigMatStep
+
+        steps = []
+        self._csd_steps(np.asarray(s.matrix, dtype=np.complex128), [int(p) for p in s.positions], int(s.cmask), int(s.cval), steps)
+        real = np.float32 if self.dtype == QB2_C64 else np.float64
+        for st in steps:
+            if st[0] == "tc":
+                self._run_block_tc(BigMatStep(st[1], st[2], st[3], st[4]))
+                self.stats["big"] -= 1
+            else:
+                _kind, target, ctrl, theta, cmask, cval = st
+                cs = np.stack([np.cos(theta), np.sin(theta)], axis=1).astype(real)
+                dev = self._upload_bytes(cs.tobytes())
+                arr = (ctypes.c_int * len(ctrl))(*ctrl)
+                _lib.check(
+                    self.lib.qb2_apply_mux_ry(self._raw_state().data_ptr(), self.n, self.hi_base, target, arr, len(ctrl), dev.data_ptr(),
+                                              cmask, cval, self.dtype, self._stream()),
+                    "qb2_apply_mux_ry",
+                )
+        self.stats["big"] += 1
+        self.stats["block_csd"] = self.stats.get("block_csd", 0) + 1
+
     def _run_big(self, s):
         self._materialize()
         torch = _torch()
         k = len(s.positions)
+        if (6 <= k <= 8 and self.dtype == QB2_C64 and self.n >= 12 and all(p < self.n for p in s.positions)
+                and getattr(self, "block_tc", True) and os.environ.get("QB2_NO_BLOCK_TC") is None):
+            return self._run_block_csd(s)
         if (k == 5 and self.dtype == QB2_C64 and self.n >= 12 and all(p < self.n for p in s.positions)
                 and getattr(self, "block_tc", True) and os.environ.get("QB2_NO_BLOCK_TC") is None):
             return self._run_block_tc(s)

@@ -40,3 +40,25 @@ for name, targets in (("low", [0, 1, 2, 3, 4]), ("mid", [10, 11, 12, 13, 14]), (
         out[label + "_frac_of_hbm_peak"] = round((16 << n) / (ms * 1e-3) / 1e9 / peak, 3)
     out["norm2"] = sv.norm2()
     print(json.dumps(out), flush=True)
+
+# wider blocks: cosine-sine decomposition into controlled 5-qubit tensor-core blocks + multiplexed rotations
+for k in (6, 7):
+    a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+    uk, _ = np.linalg.qr(a)
+    targets = list(range(10, 10 + k))
+    step = BigMatStep(targets, uk, 0, 0)
+    out = {"n": n, "k": k, "targets": targets}
+    for label, tc in (("tc_csd", True), ("simt", False)):
+        sv.block_tc = tc
+        sv._run_big(step)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3 if tc else 1
+        e0.record()
+        for _ in range(reps):
+            sv._run_big(step)
+        e1.record()
+        torch.cuda.synchronize()
+        out[label + "_ms"] = round(e0.elapsed_time(e1) / reps, 3)
+    out["norm2"] = sv.norm2()
+    print(json.dumps(out), flush=True)
