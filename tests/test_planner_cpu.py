@@ -568,3 +568,57 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["unit"] == "amplitude-updates/s" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_cosine_sine_steps_rebuild_the_block():
+    """Dense blocks on 6 and 7 qubits run as controlled 5-qubit blocks around multiplexed real rotations
+    (engine._csd_steps, scipy's cosine-sine decomposition): the step list, applied with numpy under the kernels'
+    index conventions (matrix index bit i <-> positions[i], controls as mask / value over the index), rebuilds
+    the unitary."""
+    from qrisp_b200.engine import DeviceOps
+
+    class Host(DeviceOps):
+        pass
+
+    rng = np.random.default_rng(1)
+    for k, positions in ((6, [2, 3, 5, 7, 8, 0]), (7, [0, 1, 2, 3, 4, 5, 6])):
+        a = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+        u, _ = np.linalg.qr(a)
+        n = max(positions) + 1
+        steps = []
+        Host()._csd_steps(u, positions, 0, 0, steps)
+        assert sum(1 for s in steps if s[0] == "tc") == 4 ** (k - 5) and sum(1 for s in steps if s[0] == "mux") == (4 ** (k - 5) - 1) // 3
+        dim = 1 << n
+        idx = np.arange(dim)
+        M = np.eye(dim, dtype=complex)
+        for st in steps:
+            on = ((idx ^ st[-1]) & st[-2]) == 0
+            if st[0] == "tc":
+                _, P, m, _cm, _cv = st
+                row = np.zeros(dim, dtype=int)
+                for t, p in enumerate(P):
+                    row |= ((idx >> p) & 1) << t
+                base = idx & ~sum(1 << p for p in P)
+                acc = np.zeros_like(M)
+                for c in range(32):
+                    dep = sum(((c >> t) & 1) << p for t, p in enumerate(P))
+                    acc += m[row, c][:, None] * M[base | dep, :]
+                new = M.copy()
+                new[on, :] = acc[on, :]
+                M = new
+            else:
+                _, tg, ctrl, theta, _cm, _cv = st
+                j = np.zeros(dim, dtype=int)
+                for c, p in enumerate(ctrl):
+                    j |= ((idx >> p) & 1) << c
+                cth, sth = np.cos(theta)[j][:, None], np.sin(theta)[j][:, None]
+                partner = M[idx ^ (1 << tg), :]
+                new = np.where((((idx >> tg) & 1) == 0)[:, None], cth * M - sth * partner, sth * partner + cth * M)
+                M = np.where(on[:, None], new, M)
+        # the block acts on `positions` of an n-qubit register: compare with the embedded unitary
+        row = np.zeros(dim, dtype=int)
+        for t, p in enumerate(positions):
+            row |= ((idx >> p) & 1) << t
+        rest = idx & ~sum(1 << p for p in positions)
+        want = np.where(rest[:, None] == rest[None, :], u[row[:, None], row[None, :]], 0)
+        assert np.abs(M - want).max() < 1e-12
