@@ -85,6 +85,38 @@ extern "C" int qb2_sparse_prefix(int n_instr, const int32_t *qoff, const int32_t
             bit[i] = 1ull << q[i];  // matrix index bit k-1-i <-> qubits[i]
             qmask |= bit[i];
         }
+        // monomial matrix (one non-zero per column: diagonal phases, CX / X ladders, controlled phases -- most gates of
+        // a state preparation or a QFT): every entry maps to exactly one entry, in place, no table
+        {
+            uint32_t rowof[4096];
+            bool mono = D <= 64;
+            for (uint32_t col = 0; col < D && mono; ++col) {
+                int nz = 0;
+                for (uint32_t row = 0; row < D; ++row) {
+                    const cplx m = M[(size_t)row * D + col];
+                    if (m.real() != 0.0 || m.imag() != 0.0) {
+                        ++nz;
+                        rowof[col] = row;
+                    }
+                }
+                mono = nz == 1;
+            }
+            if (mono) {
+                for (size_t e = 0; e < cur_i.size(); ++e) {
+                    const uint64_t x = cur_i[e];
+                    uint32_t col = 0;
+                    for (int i = 0; i < k; ++i)
+                        if (x & bit[i]) col |= 1u << (k - 1 - i);
+                    const uint32_t row = rowof[col];
+                    uint64_t y = x & ~qmask;
+                    for (int i = 0; i < k; ++i)
+                        if (row & (1u << (k - 1 - i))) y |= bit[i];
+                    cur_i[e] = y;
+                    cur_a[e] *= M[(size_t)row * D + col];
+                }
+                continue;
+            }
+        }
         tab.clear();
         bool fits = true;
         for (size_t e = 0; e < cur_i.size() && fits; ++e) {

@@ -185,6 +185,24 @@ class ShardedStateVector(DeviceOps):
             self._peers = {}
         return bool(self._peers)
 
+    def release_peers(self):
+        """Drop the mappings of the peers' shards (they keep the peers' buffers alive) and let torch's IPC
+        bookkeeping free what nobody uses any more.  Collective in spirit: every rank should call it (or drop
+        its engine) at the same point."""
+        if getattr(self, "_peer_keep", None):
+            import torch
+
+            torch.cuda.current_stream(self.device).synchronize()
+            self._peer_keep = []
+            self._peers = None
+            torch.cuda.ipc_collect()
+
+    def __del__(self):
+        try:
+            self.release_peers()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
     def _stream_barrier(self):
         """Every rank's stream has reached this point when the tiny all-reduce completes (stream ordered)."""
         self.dist.all_reduce(self._flag, group=self.group)

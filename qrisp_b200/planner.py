@@ -23,6 +23,7 @@ Everything here is host logic on small arrays; nothing touches amplitudes.
 from __future__ import annotations
 
 import os
+import math
 import struct
 
 import numpy as np
@@ -1126,17 +1127,16 @@ def _fit_multipliers(terms, regpos, frac_bits):
     table: phase = c * (index bits).  Returns (multiplier entries, remaining terms)."""
     mod = 1 << frac_bits
     cands, rest = [], []
+    scale = 4294967296.0 * (4294967296.0 if frac_bits == 64 else 1.0)
     for positions, turns in terms:
         if len(positions) == 2:
-            ib = positions.index(regpos)
-            t = turns.reshape(2, 2)  # [bit1, bit0]
-            t = t if ib == 1 else t.T  # -> [x_b, x_a]
-            z = np.exp(2j * np.pi * t)
-            if abs(z[0, 0] - 1) < 1e-15 and abs(z[0, 1] - 1) < 1e-15 and abs(z[1, 0] - 1) < 1e-15:
+            # (plain floats: this runs once per controlled phase of the circuit)
+            ib = 0 if positions[0] == regpos else 1
+            t00, t01, t10, t11 = float(turns[0]), float(turns[1]), float(turns[2]), float(turns[3])  # [bit1, bit0]
+            # entries other than x_a = x_b = 1 must be whole turns (phase 1 to 1e-15)
+            if max(abs(t00 - round(t00)), abs(t01 - round(t01)), abs(t10 - round(t10))) < 1e-16:
                 a = positions[1 - ib]
-                f = int(np.rint((t[1, 1] - np.floor(t[1, 1])) * 4294967296.0 * (4294967296.0 if frac_bits == 64 else 1.0)))
-                if frac_bits == 64:
-                    f = _frac64(t[1, 1])
+                f = _frac64(t11) if frac_bits == 64 else int(round((t11 - math.floor(t11)) * scale))
                 cands.append((a, f % mod, [(positions, turns)]))
                 continue
         rest.append((positions, turns))
