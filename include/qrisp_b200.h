@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QB2_ABI_VERSION 9
+#define QB2_ABI_VERSION 10
 
 #define QB2_C64 0
 #define QB2_C128 1
@@ -127,6 +127,16 @@ int qb2_apply_matrix_big(const void *src, void *dst, int n, uint64_t hi_base, co
                          const int *targets, int k, uint64_t ctrl_mask, uint64_t ctrl_value, int dtype,
                          void *stream);
 
+/* qb2_run_pass with its two optional extras: `jit_kernel` (see below; null = the interpreter) and
+ * `tile_norms_dev` -- DEVICE array of 2**(n - T) doubles that receives, for every tile the pass stores, the sum
+ * of |amp|**2 over the tile (null = off).  When the tile is the lowest T positions, entry t covers the amplitudes
+ * [t << T, (t + 1) << T): exactly the first level of the sampler (qb2_sample_scan + qb2_sample_draw_chunks with
+ * chunk_bits = T), which then needs no read of the whole state (reference: the abs**2 reduction of
+ * bi_arrays.py:1030-1059 fused into the kernel that produces the amplitudes).  Tiles a sparse-input pass does not
+ * visit are not written: hand in zeros. */
+int qb2_run_pass_ex(void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev, int dtype, void *stream,
+                    const void *sparse_dev, uint32_t n_sparse, void *jit_kernel, double *tile_norms_dev);
+
 /* Specialised pass kernels.  The host may compile, for ONE pass, a kernel whose descriptors are compile-time
  * constants (qrisp_b200/jit.py writes the translation unit -- phases, op records, decode schedule and slot maps
  * as constexpr tables, then csrc/qb2_pass_tma.cuh or csrc/qb2_pass_kernel.cuh -- and runs `nvcc -cubin
@@ -212,6 +222,12 @@ int qb2_sample_chunk_bits(int n);
 int qb2_sample_prepare(const void *state, int n, double *chunk_sums_dev, int dtype, void *stream);
 int qb2_sample_draw(const void *state, int n, const double *chunk_sums_dev, const double *uniforms_dev,
                     int64_t shots, uint64_t *indices_dev, int dtype, void *stream);
+/* The same two steps with the first level supplied by the caller: an in-place inclusive scan of `count` chunk
+ * sums, and the draw with an explicit chunk size (2**chunk_bits amplitudes per chunk, chunk c = amplitudes
+ * [c << chunk_bits, ...)). */
+int qb2_sample_scan(double *sums_dev, uint64_t count, void *stream);
+int qb2_sample_draw_chunks(const void *state, int n, int chunk_bits, const double *chunk_sums_dev, const double *uniforms_dev,
+                           int64_t shots, uint64_t *indices_dev, int dtype, void *stream);
 
 /* ---------------------------------------------------------------- packed pass layout
  * All offsets are bytes from the start of the blob; the blob is 256-byte aligned on the

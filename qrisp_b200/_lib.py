@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libqb2.so")
 
-QB2_ABI_VERSION = 9
+QB2_ABI_VERSION = 10
 QB2_BLOCK_TC_BYTES = 32768  # include/qrisp_b200.h
 QB2_C64, QB2_C128 = 0, 1
 QB2_NO_BASIS = (1 << 64) - 1
@@ -41,6 +41,16 @@ SYMBOLS = {
     "qb2_run_pass": (
         _c.c_int,
         [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32],
+    ),
+    "qb2_run_pass_ex": (
+        _c.c_int,
+        [_c.c_void_p, _c.c_int, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32,
+         _c.c_void_p, _c.c_void_p],
+    ),
+    "qb2_sample_scan": (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    "qb2_sample_draw_chunks": (
+        _c.c_int,
+        [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p],
     ),
     "qb2_jit_load": (_c.c_int, [_c.c_char_p, _c.POINTER(_c.c_void_p)]),
     "qb2_run_pass_jit": (

@@ -115,6 +115,21 @@ int qb2_run_pass(void *state, int n, uint64_t hi_base, const void *header, const
                        (cudaStream_t)stream, sparse_dev, n_sparse);
 }
 
+int qb2_run_pass_ex(void *state, int n, uint64_t hi_base, const void *header, const void *blob_dev, int dtype, void *stream,
+                    const void *sparse_dev, uint32_t n_sparse, void *jit_kernel, double *tile_norms_dev) {
+    if (int rc = check_dtype(dtype, "qb2_run_pass_ex")) return rc;
+    return launch_pass(state, n, hi_base, reinterpret_cast<const qb2_pass_header *>(header), blob_dev, dtype,
+                       (cudaStream_t)stream, sparse_dev, n_sparse, jit_kernel, tile_norms_dev);
+}
+
+int qb2_sample_scan(double *sums_dev, uint64_t count, void *stream) { return launch_scan_sums(sums_dev, count, (cudaStream_t)stream); }
+
+int qb2_sample_draw_chunks(const void *state, int n, int chunk_bits, const double *chunk_sums_dev, const double *uniforms_dev,
+                           int64_t shots, uint64_t *indices_dev, int dtype, void *stream) {
+    if (int rc = check_dtype(dtype, "qb2_sample_draw_chunks")) return rc;
+    return launch_sample_draw_cb(state, n, chunk_bits, chunk_sums_dev, uniforms_dev, shots, indices_dev, dtype, (cudaStream_t)stream);
+}
+
 int qb2_jit_load(const char *cubin_path, void **kernel_out) {
     if (!cubin_path || !kernel_out) return set_error(QB2_EINVAL, "qb2_jit_load: null pointer");
     // driver API through the runtime's entry-point lookup (no link against libcuda): the module lives in the

@@ -48,6 +48,8 @@ struct SparseInput {
     const uint32_t *loc;   // [count]
     const void *amp;       // [count] amplitudes in the pass dtype
     uint32_t count;
+    // (rides along: the per-launch extras of a pass travel in this one by-value struct)
+    double *tile_norms;    // [tiles] sum of |amp|**2 of every tile as it is stored, or null
 };
 
 struct PassLaunch {
@@ -72,7 +74,12 @@ QB2_DECLARE_VARIANT(10) QB2_DECLARE_VARIANT(11) QB2_DECLARE_VARIANT(12) QB2_DECL
 
 // launchers implemented per translation unit
 int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, int dtype,
-                cudaStream_t s, const void *sparse_dev, uint32_t n_sparse, const void *jit_kernel = nullptr);
+                cudaStream_t s, const void *sparse_dev, uint32_t n_sparse, const void *jit_kernel = nullptr,
+                double *tile_norms_dev = nullptr);
+int launch_chunk_sums(const void *state, int n, int cb, double *sums_dev, int dtype, cudaStream_t s);
+int launch_scan_sums(double *sums_dev, uint64_t count, cudaStream_t s);
+int launch_sample_draw_cb(const void *state, int n, int cb, const double *chunk_sums_dev, const double *uniforms_dev, int64_t shots,
+                          uint64_t *indices_dev, int dtype, cudaStream_t s);
 int launch_init_sparse(void *state, int n, const uint64_t *idx_dev, const void *amp_dev, uint32_t count, int dtype,
                        cudaStream_t s);
 int launch_init_basis(void *state, int n, uint64_t basis, int dtype, cudaStream_t s);

@@ -573,12 +573,35 @@ int launch_sample_prepare(const void *state, int n, double *chunk_sums_dev, int 
     return launch_scan(chunk_sums_dev, nchunks, s);
 }
 
+int launch_chunk_sums(const void *state, int n, int cb, double *sums_dev, int dtype, cudaStream_t s) {
+    if (!state || !sums_dev || cb < 0 || cb > n) return set_error(QB2_EINVAL, "chunk sums: bad arguments");
+    const uint64_t nchunks = 1ull << (n - cb);
+    uint64_t blocks = nchunks;
+    const uint64_t cap = (uint64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == QB2_C64)
+        chunk_sums_kernel<float2><<<(unsigned)blocks, SAMPLE_THREADS, 0, s>>>((const float2 *)state, cb, nchunks, sums_dev);
+    else
+        chunk_sums_kernel<double2><<<(unsigned)blocks, SAMPLE_THREADS, 0, s>>>((const double2 *)state, cb, nchunks, sums_dev);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "chunk_sums launch");
+}
+
+int launch_scan_sums(double *sums_dev, uint64_t count, cudaStream_t s) {
+    if (!sums_dev || count < 1) return set_error(QB2_EINVAL, "qb2_sample_scan: bad arguments");
+    return launch_scan(sums_dev, count, s);
+}
+
 int launch_sample_draw(const void *state, int n, const double *chunk_sums_dev, const double *uniforms_dev,
                        int64_t shots, uint64_t *indices_dev, int dtype, cudaStream_t s) {
-    if (!state || !chunk_sums_dev || !uniforms_dev || !indices_dev || n < 0 || n > 40 || shots < 0)
+    return launch_sample_draw_cb(state, n, sample_chunk_bits(n), chunk_sums_dev, uniforms_dev, shots, indices_dev, dtype, s);
+}
+
+int launch_sample_draw_cb(const void *state, int n, int cb, const double *chunk_sums_dev, const double *uniforms_dev,
+                          int64_t shots, uint64_t *indices_dev, int dtype, cudaStream_t s) {
+    if (!state || !chunk_sums_dev || !uniforms_dev || !indices_dev || n < 0 || n > 40 || shots < 0 || cb < 0 || cb > n || cb > 20)
         return set_error(QB2_EINVAL, "qb2_sample_draw: bad arguments");
     if (shots == 0) return QB2_OK;
-    const int cb = sample_chunk_bits(n);
     const uint64_t nchunks = 1ull << (n - cb);
     uint64_t blocks = (uint64_t)shots;
     const uint64_t cap = (uint64_t)sm_count() * 8;

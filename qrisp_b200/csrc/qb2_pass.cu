@@ -83,7 +83,7 @@ typedef int (*variant_fn)(const PassLaunch &);
 }  // namespace
 
 int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, const void *blob_dev, int dtype, cudaStream_t s,
-                const void *sparse_dev, uint32_t n_sparse, const void *jit_kernel) {
+                const void *sparse_dev, uint32_t n_sparse, const void *jit_kernel, double *tile_norms_dev) {
     if (!state || !h || !blob_dev) return set_error(QB2_EINVAL, "qb2_run_pass: null pointer");
     if (h->magic != QB2_PASS_MAGIC) return set_error(QB2_EINVAL, "qb2_run_pass: bad magic 0x%08x", h->magic);
     if ((int)h->dtype != dtype) return set_error(QB2_EINVAL, "qb2_run_pass: pass dtype %d != state dtype %d", h->dtype, dtype);
@@ -110,6 +110,7 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
     L.sparse.loc = nullptr;
     L.sparse.amp = nullptr;
     L.sparse.count = 0;
+    L.sparse.tile_norms = tile_norms_dev;
     L.jit_kernel = jit_kernel;
     if (h->features & QB2_FEATURE_ZERO_INPUT) {
         if (n_sparse > QB2_MAX_SPARSE) return set_error(QB2_ELIMIT, "qb2_run_pass: %u sparse input entries (at most %d)", n_sparse, QB2_MAX_SPARSE);
@@ -149,7 +150,12 @@ int launch_pass(void *state, int n, uint64_t hi_base, const qb2_pass_header *h, 
         else if (h->r == 4 && tb <= 8) geom = 5;
     }
     if (geom < 0) return set_error(QB2_ELIMIT, "qb2_run_pass: no kernel variant for dtype=%d r=%u T=%u", dtype, h->r, h->T);
-    return table[2 * geom + full](L);
+    // the register-pipelined kernel does not write tile norms: a separate read of the state fills them (the caller
+    // asked for them under the contract "tile t = amplitudes [t << T, (t + 1) << T)")
+    L.sparse.tile_norms = nullptr;
+    if (int rc = table[2 * geom + full](L)) return rc;
+    if (tile_norms_dev) return launch_chunk_sums(state, n, (int)h->T, tile_norms_dev, dtype, s);
+    return QB2_OK;
 }
 
 namespace {

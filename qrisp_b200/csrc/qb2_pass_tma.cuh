@@ -117,6 +117,7 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
         roots[i] = make_float2(c, s);
     }
     uint64_t *const full_bar = reinterpret_cast<uint64_t *>(aux + NROOT * sizeof(vec));  // [2]: one per group
+    float *const norm_part = reinterpret_cast<float *>(full_bar + 2);                    // [2 groups][8 warps]
 
     const qb2_pass_header *const H = reinterpret_cast<const qb2_pass_header *>(pb);
     const qb2_phase *const phases = reinterpret_cast<const qb2_phase *>(pb + H->phases_off);
@@ -401,9 +402,28 @@ __device__ __forceinline__ void pass_tma_body(const CUtensorMap &tmap, const uin
             asm volatile("" : "+r"(wb_t));
             smem_store_any<RB, TMA_WIN>(wb_t, (io_xf & 1u) != 0u, io_xf >> 8 & 0xffu, io_wcols, a);
         }
+        if (SP.tile_norms) {
+            // |amp|**2 of the tile as it leaves (the sampler's first level: saves its read of the whole state)
+            float part = 0.f;
+            static_for<0, NR>([&](auto J) {
+                constexpr int j = decltype(J)::value;
+                part = fmaf(a[j].x, a[j].x, fmaf(a[j].y, a[j].y, part));
+            });
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if ((tid & 31u) == 0u) norm_part[g * 8u + (tid >> 5)] = part;
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         group_bar(g);
-        if (tid == 0) tma_store_tile(&tmap, gbuf, (int)(tbase >> 4));
+        if (tid == 0) {
+            tma_store_tile(&tmap, gbuf, (int)(tbase >> 4));
+            if (SP.tile_norms) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) sum += (double)norm_part[g * 8u + w];
+                SP.tile_norms[t] = sum;
+            }
+        }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -494,7 +514,7 @@ int launch_kernel_tma(const PassLaunch &L) {
             return set_error(QB2_ELIMIT, "tma: the driver has no cuTensorMapEncodeTiled");
         encode = reinterpret_cast<tensor_map_encode_fn>(fn);
     }
-    const uint32_t ctx_off = NROOT * sizeof(float2) + 64u;
+    const uint32_t ctx_off = NROOT * sizeof(float2) + 128u;  // roots, then 2 barriers + 16 partial norms
     const uint32_t slot_off = ctx_off + h->n_phases * TMA_GROUP * 8u;
     if (h->n_slots > QB2_MAX_SLOTS) return set_error(QB2_ELIMIT, "pass uses %u phase slots (at most %d)", h->n_slots, QB2_MAX_SLOTS);
     // slots whose ladders read no bit outside the tile: their phase does not change from tile to tile, the kernel

@@ -120,23 +120,25 @@ class DeviceOps:
             # True: compiled once per pass structure (seconds), then cached; None (the default): only what the
             # cache already holds -- a kernel somebody has paid for is used, nothing is ever compiled unasked
             kernel = step.jit = jit.kernel_for(step, build=mode is True)
-        if kernel:
-            _lib.check(
-                self.lib.qb2_run_pass_jit(
-                    kernel, self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype,
-                    self._stream(), sp_ptr, sp_count,
-                ),
-                "qb2_run_pass_jit",
-            )
-            self.stats["jit_passes"] = self.stats.get("jit_passes", 0) + 1
-            return
+        # the last pass of a plan, when its tile is the lowest T positions, also leaves the per-tile |amp|**2 sums:
+        # the sampler's first level, for free (see sample())
+        self._norms = None
+        norms = None
+        T = len(step.tile_pos)
+        if (getattr(step, "last", False) and getattr(self, "fuse_norms", True) and self.hi_base == 0 and self.n > T
+                and list(step.tile_pos) == list(range(T))):
+            norms = _torch().zeros(1 << (self.n - T), dtype=_torch().float64, device=self.device)
         _lib.check(
-            self.lib.qb2_run_pass(
+            self.lib.qb2_run_pass_ex(
                 self._raw_state().data_ptr(), self.n, self.hi_base, header, dev.data_ptr() + offset, self.dtype, self._stream(),
-                sp_ptr, sp_count,
+                sp_ptr, sp_count, kernel, norms.data_ptr() if norms is not None else None,
             ),
             "qb2_run_pass",
         )
+        if kernel:
+            self.stats["jit_passes"] = self.stats.get("jit_passes", 0) + 1
+        if norms is not None:
+            self._norms = (norms, T)
 
     def _raw_state(self):
         """The amplitude buffer as it is (a pass may run on a state whose zeros were never written)."""
@@ -146,6 +148,7 @@ class DeviceOps:
         """Write the pending sparse state for real (see :meth:`StateVector.reset`)."""
         pending = getattr(self, "_pending", None)
         if pending is not None:
+            self._norms = None
             self._pending = None
             self._init_sparse(pending)
 
@@ -184,6 +187,7 @@ class DeviceOps:
 
     def _run_block_tc(self, s):
         """A dense 5-qubit block on the tensor cores (qb2_apply_block_tc: tcgen05.mma, TF32 x 3), in place."""
+        self._norms = None
         order = np.argsort(s.positions)
         positions = [int(s.positions[i]) for i in order]
         old = np.arange(32)
@@ -251,6 +255,7 @@ class DeviceOps:
 
     def _run_big(self, s):
         self._materialize()
+        self._norms = None
         torch = _torch()
         k = len(s.positions)
         if (6 <= k <= 8 and self.dtype == QB2_C64 and self.n >= 12 and all(p < self.n for p in s.positions)
@@ -342,6 +347,7 @@ class StateVector(DeviceOps):
         dense pass builds its tiles from it instead of reading 2**n zeros; anything else that looks at
         the buffer first makes :meth:`_materialize` write it."""
         self._pending = prefix.zero_state()
+        self._norms = None
         # no data sits in HBM any more, so the qubit map is free again: back to the canonical one (a
         # reset engine is a new engine; compiled programs name the map they start from)
         nq = self.num_qubits
@@ -499,20 +505,29 @@ class StateVector(DeviceOps):
         shots = len(uniforms)
         if qubits is None:
             qubits = list(range(self.num_qubits))
-        cb = self.lib.qb2_sample_chunk_bits(self.n)
-        sums = torch.empty(1 << (self.n - cb), dtype=torch.float64, device=self.device)
-        _lib.check(
-            self.lib.qb2_sample_prepare(self.state.data_ptr(), self.n, sums.data_ptr(), self.dtype, self._stream()),
-            "qb2_sample_prepare",
-        )
+        fused = getattr(self, "_norms", None)
+        if fused is not None:
+            # the last pass left the per-tile |amp|**2 sums: no read of the whole state (a copy is scanned, the sums
+            # stay valid for further calls)
+            cb = fused[1]
+            sums = fused[0].clone()
+            _lib.check(self.lib.qb2_sample_scan(sums.data_ptr(), sums.numel(), self._stream()), "qb2_sample_scan")
+            self.stats["fused_norms"] = self.stats.get("fused_norms", 0) + 1
+        else:
+            cb = self.lib.qb2_sample_chunk_bits(self.n)
+            sums = torch.empty(1 << (self.n - cb), dtype=torch.float64, device=self.device)
+            _lib.check(
+                self.lib.qb2_sample_prepare(self.state.data_ptr(), self.n, sums.data_ptr(), self.dtype, self._stream()),
+                "qb2_sample_prepare",
+            )
         u_dev = torch.from_numpy(uniforms).to(self.device)
         idx = torch.empty(shots, dtype=torch.int64, device=self.device)
         _lib.check(
-            self.lib.qb2_sample_draw(
-                self.state.data_ptr(), self.n, sums.data_ptr(), u_dev.data_ptr(), shots, idx.data_ptr(), self.dtype,
+            self.lib.qb2_sample_draw_chunks(
+                self.state.data_ptr(), self.n, cb, sums.data_ptr(), u_dev.data_ptr(), shots, idx.data_ptr(), self.dtype,
                 self._stream(),
             ),
-            "qb2_sample_draw",
+            "qb2_sample_draw_chunks",
         )
         self.io["h2d"] += uniforms.nbytes
         self.io["d2h"] += shots * 8

@@ -236,6 +236,7 @@ class PassStep:
         # phase's distribution (register positions, thread positions)
         self.segs, self.R0, self.TP0 = list(segs), list(R0), list(TP0)
         self.tma = tma
+        self.last = False
 
 
 def tma_tile_ok(tile_pos, n):
@@ -373,6 +374,8 @@ class Planner:
                 nxt = next((op for op in rest if op.kind != "relabel"), None)
                 settle = nxt is None or (nxt.kind == "mat" and len(nxt.targets) > cfg.max_mat)
                 built = self._build_passes(resolved, settle)[0]
+                if nxt is None and built and built[-1].kind == "pass":
+                    built[-1].last = True  # nothing follows: the engine may ask this pass for its per-tile norms
                 steps.extend(built)
                 if on_step is not None:
                     for st in built:
