@@ -125,7 +125,7 @@ class DeviceOps:
         self._norms = None
         norms = None
         T = len(step.tile_pos)
-        if (getattr(step, "last", False) and getattr(self, "fuse_norms", True) and self.hi_base == 0 and self.n > T
+        if (getattr(step, "last", False) and getattr(self, "fuse_norms", True) and getattr(self, "world", 1) == 1 and self.n > T
                 and list(step.tile_pos) == list(range(T))):
             norms = _torch().zeros(1 << (self.n - T), dtype=_torch().float64, device=self.device)
         _lib.check(
