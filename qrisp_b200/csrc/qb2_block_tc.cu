@@ -138,8 +138,24 @@ __global__ void __launch_bounds__(TC_G *TC_M, 1)
             const int p = T.t[i];
             idx = ((idx >> p) << (p + 1)) | (idx & ((1ull << p) - 1ull));
         }
-        // a column the controls switch off is neither loaded nor stored (its accumulator row is garbage)
+        // a column the controls switch off is neither loaded nor stored (its accumulator row is garbage); a tile
+        // in which no column is active (controls above the tile's column bits: the usual case) is skipped by the
+        // whole group -- one barrier with an OR reduction
         const bool active = (((idx | hi_base) ^ cval) & cmask) == 0ull;
+        if (cmask != 0ull) {
+            uint32_t any;
+            asm volatile(
+                "{\n"
+                ".reg .pred p, q;\n"
+                "setp.ne.u32 q, %1, 0;\n"
+                "bar.red.or.pred p, %2, %3, q;\n"
+                "selp.u32 %0, 1, 0, p;\n"
+                "}\n"
+                : "=r"(any)
+                : "r"((uint32_t)active), "r"(g + 1u), "n"(TC_M)
+                : "memory");
+            if (!any) continue;
+        }
         float2 *const base = state + idx;
         if (active) {
 #pragma unroll

@@ -185,9 +185,13 @@ class DeviceOps:
             self.stats["gate_ops"] += consumed
         return instructions[consumed:]
 
-    def _run_block_tc(self, s):
-        """A dense 5-qubit block on the tensor cores (qb2_apply_block_tc: tcgen05.mma, TF32 x 3), in place."""
-        self._norms = None
+    def _prepare_block_tc(self, s):
+        """Host side of a 5-qubit tensor-core block: targets sorted by position, the matrix re-indexed to match,
+        split into its two TF32 halves in the kernel's layout (qb2_pack_block_tc) and uploaded.  Kept on the
+        step: a replayed program pays it once."""
+        ready = getattr(s, "_tc_ready", None)
+        if ready is not None and ready[0] is self:
+            return ready[1:]
         order = np.argsort(s.positions)
         positions = [int(s.positions[i]) for i in order]
         old = np.arange(32)
@@ -200,6 +204,16 @@ class DeviceOps:
         _lib.check(self.lib.qb2_pack_block_tc(np.ascontiguousarray(m).ctypes.data, packed.ctypes.data), "qb2_pack_block_tc")
         dev = self._upload_bytes(packed.tobytes())
         tg = (ctypes.c_int * 5)(*positions)
+        try:
+            s._tc_ready = (self, dev, tg)
+        except AttributeError:
+            pass
+        return dev, tg
+
+    def _run_block_tc(self, s):
+        """A dense 5-qubit block on the tensor cores (qb2_apply_block_tc: tcgen05.mma, TF32 x 3), in place."""
+        self._norms = None
+        dev, tg = self._prepare_block_tc(s)
         _lib.check(
             self.lib.qb2_apply_block_tc(self._raw_state().data_ptr(), self.n, self.hi_base, dev.data_ptr(), tg, s.cmask, s.cval,
                                         self._stream()),
@@ -230,26 +244,40 @@ class DeviceOps:
 
     def _run_block_csd(self, s):
         """A dense block on 6..8 qubits: controlled 5-qubit blocks on the tensor cores around multiplexed real
-        rotations (qb2_apply_mux_ry), from the cosine-sine decomposition of the matrix (host, scipy)."""
+        rotations (qb2_apply_mux_ry), from the cosine-sine decomposition of the matrix (host, scipy).  The
+        decomposition and its device operands are kept on the step: a replayed program pays them once."""
         from .planner import BigMatStep
 
-        steps = []
-        self._csd_steps(np.asarray(s.matrix, dtype=np.complex128), [int(p) for p in s.positions], int(s.cmask), int(s.cval), steps)
-        real = np.float32 if self.dtype == QB2_C64 else np.float64
-        for st in steps:
+        ready = getattr(s, "_csd_ready", None)
+        if ready is None or ready[0] is not self:
+            steps = []
+            self._csd_steps(np.asarray(s.matrix, dtype=np.complex128), [int(p) for p in s.positions], int(s.cmask), int(s.cval), steps)
+            real = np.float32 if self.dtype == QB2_C64 else np.float64
+            prepared = []
+            for st in steps:
+                if st[0] == "tc":
+                    prepared.append(("tc", BigMatStep(st[1], st[2], st[3], st[4])))
+                else:
+                    _kind, target, ctrl, theta, cmask, cval = st
+                    cs = np.stack([np.cos(theta), np.sin(theta)], axis=1).astype(real)
+                    prepared.append(("mux", target, (ctypes.c_int * len(ctrl))(*ctrl), len(ctrl), self._upload_bytes(cs.tobytes()), cmask, cval))
+            ready = (self, prepared)
+            try:
+                s._csd_ready = ready
+            except AttributeError:
+                pass
+        for st in ready[1]:
             if st[0] == "tc":
-                self._run_block_tc(BigMatStep(st[1], st[2], st[3], st[4]))
+                self._run_block_tc(st[1])
                 self.stats["big"] -= 1
             else:
-                _kind, target, ctrl, theta, cmask, cval = st
-                cs = np.stack([np.cos(theta), np.sin(theta)], axis=1).astype(real)
-                dev = self._upload_bytes(cs.tobytes())
-                arr = (ctypes.c_int * len(ctrl))(*ctrl)
+                _kind, target, arr, nc, dev, cmask, cval = st
                 _lib.check(
-                    self.lib.qb2_apply_mux_ry(self._raw_state().data_ptr(), self.n, self.hi_base, target, arr, len(ctrl), dev.data_ptr(),
+                    self.lib.qb2_apply_mux_ry(self._raw_state().data_ptr(), self.n, self.hi_base, target, arr, nc, dev.data_ptr(),
                                               cmask, cval, self.dtype, self._stream()),
                     "qb2_apply_mux_ry",
                 )
+        self._norms = None
         self.stats["big"] += 1
         self.stats["block_csd"] = self.stats.get("block_csd", 0) + 1
 
