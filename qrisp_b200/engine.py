@@ -94,9 +94,11 @@ class DeviceOps:
         data, count = prefix.sparse_input_list(step, phys, amp, self.n, self.hi_base, self.np_dtype)
         return (self._upload_bytes(data) if count else None), count
 
-    def _run_pass(self, step, header, dev, offset, sparse=None):
+    def _run_pass(self, step, header, dev, offset, sparse=None, norms=False):
         """``sparse``: a ready ``(device list, count)`` for a pass that starts from the pending state
-        (a replayed program keeps it resident); built here otherwise."""
+        (a replayed program keeps it resident); built here otherwise.  ``norms``: let the last pass of a plan
+        leave the sampler's per-tile sums (the streaming path of ``run()`` asks for them; a replayed program
+        does when its ``want_norms`` is set)."""
         sp_ptr, sp_count = None, 0
         pending = getattr(self, "_pending", None)
         if pending is not None:
@@ -123,9 +125,9 @@ class DeviceOps:
         # the last pass of a plan, when its tile is the lowest T positions, also leaves the per-tile |amp|**2 sums:
         # the sampler's first level, for free (see sample())
         self._norms = None
-        norms = None
+        want, norms = norms, None
         T = len(step.tile_pos)
-        if (getattr(step, "last", False) and getattr(self, "fuse_norms", True) and getattr(self, "world", 1) == 1 and self.n > T
+        if (want and getattr(step, "last", False) and getattr(self, "fuse_norms", True) and getattr(self, "world", 1) == 1 and self.n > T
                 and list(step.tile_pos) == list(range(T))):
             norms = _torch().zeros(1 << (self.n - T), dtype=_torch().float64, device=self.device)
         _lib.check(
@@ -432,7 +434,7 @@ class StateVector(DeviceOps):
                 header = ctypes.create_string_buffer(step.blob[:small], small)
                 dev = self._upload_blobs([step], [0], len(step.blob))
                 keep.append((dev, header))
-                self._run_pass(step, header, dev, 0)
+                self._run_pass(step, header, dev, 0, norms=True)
                 self.stats["passes"] += 1
                 self.stats["kernel_ops"] += step.n_ops
                 self.stats["gate_ops"] += step.n_gate_ops
@@ -603,6 +605,7 @@ class Program:
                 self._headers.append(ctypes.create_string_buffer(s.blob[:small], small))
             else:
                 self._headers.append(None)
+        self.want_norms = False  # True: the last pass also leaves the sampler's per-tile sums (see StateVector.sample)
         self._entry_sparse = None
         if entry is not None and steps and steps[0].kind == "pass":
             sv._entry_pos = self.pos_in  # the first pass sees the entry map (relabels come later)
@@ -642,7 +645,7 @@ class Program:
         first = True
         for s, o, h in zip(self.steps, self.offsets, self._headers):
             if s.kind == "pass":
-                sv._run_pass(s, h, self.dev, o, sparse=self._entry_sparse if first else None)
+                sv._run_pass(s, h, self.dev, o, sparse=self._entry_sparse if first else None, norms=self.want_norms)
             else:
                 sv._run_big(s)
             first = False

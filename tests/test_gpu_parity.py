@@ -225,6 +225,34 @@ def test_sampling_chi_square():
     assert np.all(outs == int("10000000010", 2))
 
 
+def test_replayed_program_can_leave_the_sampler_sums():
+    """``Program.want_norms``: the last pass also writes the per-tile sums the sampler starts from; the draws
+    are those of the separate reduction (same seed)."""
+    from qrisp_b200.engine import StateVector
+
+    n = 18
+    qc = random_circuit(n, 2, seed=8)
+    rng = np.random.default_rng(1)
+    for first in (0, 1):  # two brick layers on qubits 0..12: the plan ends with a pass over the lowest 13 positions
+        for q in range(first, 12, 2):
+            a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+            qc.unitary(np.linalg.qr(a)[0], [q, q + 1])
+    instrs = [i for i in qc.data if i.matrix is not None]
+    draws = []
+    for want in (False, True):
+        sv = StateVector(n)
+        prog = sv.compile(instrs)
+        prog.want_norms = want
+        sv.reset()
+        prog.run()
+        if not want:
+            assert sv._norms is None
+        draws.append(sv.sample(5000, list(range(n)), rng=np.random.default_rng(5)))
+        used = sv.stats.get("fused_norms", 0)
+    assert used >= 1, "the sampler did not start from the pass's sums"
+    assert np.array_equal(draws[0], draws[1])
+
+
 def test_wide_sampling_path(sim):
     """More measured qubits than the dense-distribution limit: counts come from the
     device sampler (GHZ: only all-zeros / all-ones)."""

@@ -81,7 +81,7 @@ def _worker(rank, world, port, case, out_dir):
             def _upload_blobs(self, steps, offs, total):
                 return None
 
-            def _run_pass(self, step, header, dev, offset, sparse=None):
+            def _run_pass(self, step, header, dev, offset, sparse=None, norms=False):
                 lst = None
                 if self._pending is not None:
                     lst = (sparse if sparse is not None else self._sparse_for(step, self._pending))[0]
