@@ -225,11 +225,39 @@ class ShardedStateVector(DeviceOps):
     def compile(self, instructions):
         """Host prefix on the pending sparse state, then plan with swaps (every rank computes the same)."""
         start = getattr(self, "_pending", None)
-        instructions = self._take_prefix(list(instructions))
-        entry = getattr(self, "_pending", None)
         unit_tol = 1e-6 if self.dtype == QB2_C64 else 1e-13
-        ops = normalize_circuit(instructions, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
+        ops = None
+        if start is not None and self.g > 0 and getattr(self, "prefix_support", None) is None and os.environ.get("QB2_PREFIX_SUPPORT") is None:
+            # A pass takes QB2_MAX_SPARSE entries PER RANK.  The qubits the prefix spreads out are never dense
+            # targets afterwards, so the initial layout puts them on the rank bits and every rank holds 1/world
+            # of the list: the host walk may go `world` times further (log2(world) more qubits absorbed -- what
+            # keeps GHZ + QFT at two passes however many ranks widen the register).  Checked, not assumed:
+            # if some rank's share came out too long, the walk is redone with the single-rank limit.
+            stats = dict(self.stats)
+            rest = self._take_prefix(list(instructions), prefix.MAX_SUPPORT * self.world)
+            ops = normalize_circuit(rest, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
+            if self._largest_share(ops) > prefix.MAX_SUPPORT:
+                self._pending, ops = start, None
+                self.stats.clear()
+                self.stats.update(stats)
+        if ops is None:
+            rest = self._take_prefix(list(instructions))
+            ops = normalize_circuit(rest, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
+        entry = getattr(self, "_pending", None)
         return self.compile_ops(ops, start=start, entry=entry)
+
+    def _largest_share(self, ops):
+        """Entries of the pending list the fullest rank would hold under the initial layout ``compile_ops``
+        is going to choose for ``ops`` (the map is put back)."""
+        idx, _ = self._pending
+        saved = list(self.pos)
+        if os.environ.get("QB2_NO_INITIAL_LAYOUT") is None:
+            self._choose_initial_layout(ops)
+        phys = prefix.to_physical(idx, self.pos, len(self.pos))
+        self.pos[:] = saved
+        if not len(phys):
+            return 0
+        return int(np.bincount((phys >> np.uint64(self.n)).astype(np.int64), minlength=1).max())
 
     def compile_ops(self, ops, start=None, entry=None):
         """Plan with swaps.  Returns the program; map and state stay what they were (``run`` moves them)."""

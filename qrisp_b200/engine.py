@@ -174,13 +174,16 @@ class DeviceOps:
             ip = ap = None
         _lib.check(self.lib.qb2_init_sparse(buf.data_ptr(), self.n, ip, ap, count, self.dtype, self._stream()), "qb2_init_sparse")
 
-    def _take_prefix(self, instructions):
+    def _take_prefix(self, instructions, support=None):
         """Evolve the pending sparse state through a prefix of ``instructions`` on the host
-        (:mod:`qrisp_b200.prefix`); returns the instructions that are left for the dense sweeps."""
+        (:mod:`qrisp_b200.prefix`); returns the instructions that are left for the dense sweeps.
+        ``support``: entries the list may grow to (default: this engine's ``prefix_support``)."""
         pending = getattr(self, "_pending", None)
         if pending is None or not instructions:
             return instructions
-        consumed, state = prefix.sparse_prefix(instructions, pending, getattr(self, "prefix_support", None))
+        if support is None:
+            support = getattr(self, "prefix_support", None)
+        consumed, state = prefix.sparse_prefix(instructions, pending, support)
         if consumed:
             self._pending = state
             self.stats["prefix_gates"] = self.stats.get("prefix_gates", 0) + consumed
