@@ -68,8 +68,13 @@ class ShardedStateVector(DeviceOps):
 
         self.dist = dist
         self.group = group if group is not None else dist.group.WORLD
-        self.world = dist.get_world_size(self.group)
-        self.rank = dist.get_rank(self.group)
+        self._init_host(num_qubits, dist.get_world_size(self.group), dist.get_rank(self.group), dtype, T, r, L, tma, prefix_support)
+        self._setup_device(device)
+        self.reset()
+
+    def _init_host(self, num_qubits, world, rank, dtype, T, r, L, tma, prefix_support):
+        """Everything the planning side needs (no device, no process group)."""
+        self.world, self.rank = int(world), int(rank)
         g = self.world.bit_length() - 1
         if 1 << g != self.world:
             raise ValueError("the number of ranks must be a power of two")
@@ -94,8 +99,6 @@ class ShardedStateVector(DeviceOps):
         self.hi_base = self.rank << self.n
         self.stats = {"passes": 0, "kernel_ops": 0, "gate_ops": 0, "phases": 0, "big": 0, "swaps": 0}
         self.io = {"h2d": 0, "d2h": 0}
-        self._setup_device(device)
-        self.reset()
 
     # ------------------------------------------------------------------ device hooks
     # (tests replace these with CPU stand-ins to exercise the sharding logic over gloo)
@@ -222,8 +225,8 @@ class ShardedStateVector(DeviceOps):
         self.state, self._scratch = self._scratch, self.state
 
     # ------------------------------------------------------------------ planning
-    def compile(self, instructions):
-        """Host prefix on the pending sparse state, then plan with swaps (every rank computes the same)."""
+    def _front_end(self, instructions):
+        """Host prefix on the pending sparse state + normalisation: ``(ops, state before, state after)``."""
         start = getattr(self, "_pending", None)
         unit_tol = 1e-6 if self.dtype == QB2_C64 else 1e-13
         ops = None
@@ -243,7 +246,11 @@ class ShardedStateVector(DeviceOps):
         if ops is None:
             rest = self._take_prefix(list(instructions))
             ops = normalize_circuit(rest, max_targets=self.cfg.max_mat, unit_tol=unit_tol)
-        entry = getattr(self, "_pending", None)
+        return ops, start, getattr(self, "_pending", None)
+
+    def compile(self, instructions):
+        """Host prefix on the pending sparse state, then plan with swaps (every rank computes the same)."""
+        ops, start, entry = self._front_end(instructions)
         return self.compile_ops(ops, start=start, entry=entry)
 
     def _largest_share(self, ops):
@@ -261,6 +268,15 @@ class ShardedStateVector(DeviceOps):
 
     def compile_ops(self, ops, start=None, entry=None):
         """Plan with swaps.  Returns the program; map and state stay what they were (``run`` moves them)."""
+        steps, pos_in, pos_before = self._plan_steps(ops)
+        prog = ShardedProgram(self, steps, pos_in=pos_in, start=start, entry=entry, pos_before=pos_before)
+        self._pending = start
+        self.pos[:] = pos_before
+        return prog
+
+    def _plan_steps(self, ops):
+        """Passes, big steps and swaps for ``ops``: ``(steps, entry map, the caller's map)``; ``self.pos`` is
+        left at the exit map."""
         pos_before = list(self.pos)
         if getattr(self, "_pending", None) is not None and self.g > 0 and os.environ.get("QB2_NO_INITIAL_LAYOUT") is None:
             # no data in HBM yet: the map is free.  The program's entry map is the chosen one.
@@ -281,10 +297,7 @@ class ShardedStateVector(DeviceOps):
             if guard > 10000:
                 raise RuntimeError("swap planning does not terminate")
             steps.append(self._plan_swap(pending, protect))
-        prog = ShardedProgram(self, steps, pos_in=pos_in, start=start, entry=entry, pos_before=pos_before)
-        self._pending = start
-        self.pos[:] = pos_before
-        return prog
+        return steps, pos_in, pos_before
 
     def _choose_initial_layout(self, ops):
         """The state is still |0...0>, which does not care which qubit sits where: the qubits that are
@@ -445,6 +458,29 @@ class ShardedStateVector(DeviceOps):
         self.dist.all_gather(shards, self.state, group=self.group)
         full = torch.cat(shards).cpu().numpy().view(self.np_dtype)
         return _canonical(full, self.pos, self.num_qubits)
+
+
+class PlanOnlyShard(ShardedStateVector):
+    """The planning half of a sharded state, without a device or a process group: what each of ``world`` ranks
+    plans for a circuit (all ranks plan the same).  For compiling specialised kernels ahead of time
+    (:func:`qrisp_b200.jit.prebuild`) and for looking at plans (``tools/dump_plan.py``); it cannot run anything."""
+
+    def __init__(self, num_qubits, world=1, dtype=np.complex64, T=None, r=None, L=4, tma=None, prefix_support=None):
+        self._init_host(num_qubits, world, 0, dtype, T, r, L, tma, prefix_support)
+        self.specialize = False
+        self._pending = prefix.zero_state()
+
+    def _setup_device(self, device):
+        raise _lib.Qb2Error("PlanOnlyShard plans; it has no device")
+
+    def plan(self, instructions):
+        """``(steps, entry state, entry map)`` for unitary ``instructions`` applied to |0...0>."""
+        self.reset()
+        ops, start, entry = self._front_end(instructions)
+        steps, pos_in, pos_before = self._plan_steps(ops)
+        self._pending = start
+        self.pos[:] = pos_before
+        return steps, entry, pos_in
 
 
 def _canonical(full, pos, nq):

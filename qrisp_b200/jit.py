@@ -327,3 +327,32 @@ def kernels_for(steps, workers=None):
         with ThreadPoolExecutor(max_workers=workers) as pool:
             list(pool.map(build, todo.items()))
     return [kernel_for(st) for st in steps]
+
+
+def prebuild(instructions, num_qubits, world=1, dtype="complex64", workers=None):
+    """Compile, WITHOUT a device, the specialised kernels of the passes ``world`` ranks would plan for the
+    unitary ``instructions`` on ``num_qubits`` qubits, into the cache (nvcc cross-compiles).  Returns
+    ``(passes, cubins present afterwards)``.  ``__graft_entry__.build()`` does this for the bench workload."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+
+    from .distributed import PlanOnlyShard
+
+    steps, _entry, _pos = PlanOnlyShard(num_qubits, world, dtype=np.dtype(dtype)).plan(list(instructions))
+    todo = {}
+    for st in steps:
+        if st.kind != "pass":
+            continue
+        small = small_section(st.blob)
+        tma = bool(getattr(st, "tma", False)) and os.environ.get("QB2_NO_TMA") is None
+        if not tma:
+            T, r, dt, _nseg = struct.unpack_from("<BBBB", small, 16)
+            if _reg_geometry(dt, r, T - r) is None:
+                continue
+        todo.setdefault(pass_key(small, tma), (small, tma))
+    workers = workers or max(1, min(16, os.cpu_count() or 1))
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        paths = list(pool.map(lambda kv: build_cubin(kv[1][0], kv[1][1], kv[0]), todo.items()))
+    return len(todo), sum(1 for p in paths if p is not None)
+

@@ -85,3 +85,17 @@ def test_specialised_translation_units_compile_for_sm_100a(tmp_path, monkeypatch
                 res = subprocess.run([cuobjdump, "-res-usage", path], capture_output=True, text=True).stdout
                 assert "qb2_pass_jit" in res and "STACK:0" in res.split("qb2_pass_jit")[1], res  # registers stay registers
     assert seen == {True, False}
+
+
+@pytest.mark.skipif(jit.find_nvcc() is None, reason="no nvcc")
+def test_prebuild_fills_the_cache_without_a_device(tmp_path, monkeypatch):
+    """What ``__graft_entry__.build()`` does for the bench workload, on a small circuit: plan as the ranks would
+    (no device, no process group), cross-compile one kernel per distinct pass structure."""
+    monkeypatch.setenv("QB2_JIT_CACHE", str(tmp_path))
+    qc = ghz_qft_circuit(22)
+    instrs = [i for i in qc.data if i.matrix is not None]
+    passes, cubins = jit.prebuild(instrs, 22, world=2)
+    assert passes >= 1 and cubins == passes
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")]) == passes
+    # a second call finds everything in the cache; another world size with the same pass structures adds nothing
+    assert jit.prebuild(instrs, 22, world=2) == (passes, cubins)

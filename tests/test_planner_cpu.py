@@ -624,38 +624,12 @@ def test_cosine_sine_steps_rebuild_the_block():
         assert np.abs(M - want).max() < 1e-12
 
 
-class _PlanOnlyShard:
-    """A ShardedStateVector reduced to what ``compile`` needs up to the plan (no device, no process group)."""
+def _plan_sharded(nq, world, instrs):
+    from qrisp_b200.distributed import PlanOnlyShard
 
-    def __new__(cls, nq, world):
-        from qrisp_b200 import prefix
-        from qrisp_b200.distributed import ShardedStateVector
-        from qrisp_b200.planner import PlanConfig
-
-        sv = object.__new__(ShardedStateVector)
-        g = world.bit_length() - 1
-        sv.g, sv.world, sv.rank, sv.n, sv.n_total, sv.num_qubits = g, world, 0, nq - g, nq, nq
-        sv.dtype, sv.hi_base = 0, 0
-        sv.cfg = PlanConfig(sv.n, T=min(13, sv.n))
-        sv.pos = [nq - 1 - q for q in range(nq)]
-        sv._pending = prefix.zero_state()
-        sv.stats = {"gate_ops": 0}
-        return sv
-
-
-def _plan_sharded(monkeypatch, nq, world, instrs):
-    import qrisp_b200.distributed as d
-
-    captured = {}
-
-    def program(sv, steps, **kw):
-        captured.update(kw, steps=steps)
-        return steps
-
-    monkeypatch.setattr(d, "ShardedProgram", program)
-    sv = _PlanOnlyShard(nq, world)
-    sv.compile(instrs)
-    return sv, captured
+    sv = PlanOnlyShard(nq, world)
+    steps, entry, pos_in = sv.plan(instrs)
+    return sv, dict(steps=steps, entry=entry, pos_in=pos_in)
 
 
 def test_sharded_host_prefix_goes_world_times_further(monkeypatch):
@@ -666,7 +640,7 @@ def test_sharded_host_prefix_goes_world_times_further(monkeypatch):
     monkeypatch.delenv("QB2_PREFIX_SUPPORT", raising=False)
     for world, nq in ((1, 30), (2, 31), (4, 32), (8, 33)):
         qc = ghz_qft_circuit(nq)
-        sv, got = _plan_sharded(monkeypatch, nq, world, [i for i in qc.data if i.matrix is not None])
+        sv, got = _plan_sharded(nq, world, [i for i in qc.data if i.matrix is not None])
         kinds = [s.kind for s in got["steps"]]
         assert kinds == ["pass", "pass"], (world, kinds)
         idx, _ = got["entry"]
@@ -676,7 +650,7 @@ def test_sharded_host_prefix_goes_world_times_further(monkeypatch):
         assert share.max() <= prefix.MAX_SUPPORT, (world, share)
     monkeypatch.setenv("QB2_PREFIX_SUPPORT", "1024")
     qc = ghz_qft_circuit(33)
-    _, got = _plan_sharded(monkeypatch, 33, 8, [i for i in qc.data if i.matrix is not None])
+    _, got = _plan_sharded(33, 8, [i for i in qc.data if i.matrix is not None])
     assert [s.kind for s in got["steps"]] == ["pass", "pass", "pass"]
 
 
@@ -694,7 +668,7 @@ def test_sharded_host_prefix_falls_back_when_a_rank_would_hold_too_much(monkeypa
         qc.cx(q, q + 1)
     for q in range(12):
         qc.h(q)
-    sv, got = _plan_sharded(monkeypatch, nq, 2, list(qc.data))
+    sv, got = _plan_sharded(nq, 2, list(qc.data))
     idx, _ = got["entry"]
     assert len(idx) <= prefix.MAX_SUPPORT
     assert sv.stats["prefix_gates"] == 10  # ten Hadamards, counted once
