@@ -340,9 +340,59 @@ class ShardedStateVector(DeviceOps):
         return SwapStep(evict, None if identity else perm)
 
     def apply_circuit(self, instructions):
-        prog = self.compile(instructions)
-        prog.run()
-        return prog
+        """Plan and run in one go, STREAMING like :meth:`StateVector.apply_circuit`: every pass is launched the
+        moment the planner has built it, every swap the moment it is decided, so the host plans step k+1 while
+        the devices work on step k.  All ranks plan the same, so their collectives line up.  Returns the steps."""
+        self._guard()
+        ops, _start, _entry = self._front_end(instructions)
+        if getattr(self, "_pending", None) is not None and self.g > 0 and os.environ.get("QB2_NO_INITIAL_LAYOUT") is None:
+            self._choose_initial_layout(ops)  # nothing in HBM yet: the map is free
+        # a pending state is laid out by the map at the entry of the plan (the planner moves ``pos`` on)
+        self._entry_pos = list(self.pos) if getattr(self, "_pending", None) is not None else None
+        planner = Planner(self.cfg, self.pos, n_total=self.n_total)
+        keep = []  # device copies of the blobs stay alive until the launches have been issued
+
+        def launch(step):
+            if step.kind == "pass":
+                small = int.from_bytes(step.blob[8:12], "little")
+                header = ctypes.create_string_buffer(step.blob[:small], small)
+                dev = self._upload_blobs([step], [0], len(step.blob))
+                keep.append((dev, header))
+                self._run_pass(step, header, dev, 0)
+                self.stats["passes"] += 1
+                self.stats["kernel_ops"] += step.n_ops
+                self.stats["gate_ops"] += step.n_gate_ops
+                self.stats["phases"] += step.n_phases
+            else:
+                self._run_big(step)
+                self.stats["gate_ops"] += 1
+            self._entry_pos = None  # the state is in HBM from here on
+
+        steps = []
+        pending = list(ops)
+        protect = set(range(self.cfg.L))
+        guard = 0
+        try:
+            while pending:
+                part, need = planner.plan(pending, on_step=launch)
+                steps.extend(part)
+                if need is None:
+                    break
+                pending = planner.pending
+                guard += 1
+                if guard > 10000:
+                    raise RuntimeError("swap planning does not terminate")
+                # (a swap on a state nobody has written yet writes it first, under the entry map: the swap
+                # is planned -- and ``pos`` moved -- only after that)
+                self._materialize()
+                self._entry_pos = None
+                swap = self._plan_swap(pending, protect)
+                self.run_swap(swap)
+                steps.append(swap)
+        finally:
+            self._entry_pos = None
+        self._keep_alive = keep
+        return steps
 
     # ------------------------------------------------------------------ execution of one swap
     def run_swap(self, step):
