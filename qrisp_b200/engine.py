@@ -107,6 +107,11 @@ class DeviceOps:
             # reading 2**n zeros, and stores all-zero tiles without running the ops
             if sparse is None:
                 sparse = self._sparse_for(step, pending)
+            if sparse[1] > prefix.MAX_SUPPORT:
+                # more entries on this rank than a pass takes (a sharded list is `world` times longer and an
+                # earlier call may have left it pending under another layout): write the state, run normally
+                self._materialize()
+                return self._run_pass(step, header, dev, offset, norms=norms)
             self._sparse_keep = sparse
             sp_ptr = sparse[0].data_ptr() if sparse[0] is not None else None
             sp_count = sparse[1]
