@@ -92,7 +92,16 @@ class B200Job:
     def status(self):
         return self._status
 
-    def done(self):
+    def done(self):  # reference: job.py:383-405 -- done() is DONE only; the terminal states are three
+        return self._status == "done"
+
+    def running(self):
+        return self._status == "running"
+
+    def cancelled(self):
+        return self._status == "cancelled"
+
+    def in_final_state(self):
         return self._status in ("done", "error", "cancelled")
 
     def cancel(self):
@@ -110,8 +119,13 @@ class B200Backend:
     :class:`qrisp_b200.circuit.Circuit`); ``shots``: int, list of ints or None (the ``shots`` option;
     None = exact probabilities, as with the reference's simulator backend)."""
 
-    def __init__(self, name=None, options=None, dtype=np.complex64, **engine_kwargs):
+    def __init__(self, name=None, options=None, dtype=np.complex64, pm=None, **engine_kwargs):
         self.name = name or "B200Simulator"
+        # reference: QrispSimulatorBackend(pm=...) -- a pass manager every circuit goes through before it is
+        # simulated; anything with a ``run(circuit) -> circuit`` method (a qrisp PassManager has one)
+        if pm is not None and not callable(getattr(pm, "run", None)):
+            raise TypeError(f"Expected a PassManager instance for 'pm', got {type(pm).__name__}.")
+        self._pm = pm
         if options is None:
             options = self._default_options()
         if not isinstance(options, Mapping):
@@ -142,8 +156,10 @@ class B200Backend:
     def run_async(self, circuits, shots=None):
         _validate_shots(shots)
         batch = list(circuits) if _is_batch(circuits) else [circuits]
+        if self._pm is not None:
+            batch = [self._pm.run(c) for c in batch]
         if isinstance(shots, list) and len(shots) != len(batch):
-            raise ValueError("one shot count per circuit")
+            raise ValueError(f"Length of 'shots' ({len(shots)}) must match the number of circuits ({len(batch)}).")
         if shots is None:
             shots = self._options.get("shots")
         job = B200Job(self, batch, shots)
@@ -159,10 +175,13 @@ class B200Backend:
         return res if _is_batch(circuits) else res[0]
 
 
-def make_qrisp_backend(dtype=np.complex64, **engine_kwargs):
+def make_qrisp_backend(dtype=np.complex64, pm=None, **engine_kwargs):
     """A ``qrisp.interface.Backend`` that simulates on the B200: assign it to
-    ``qrisp.default_backend.def_backend`` (or pass ``backend=...`` to ``get_measurement``).  Needs Qrisp
-    importable in the calling process; nothing else in this package does."""
+    ``qrisp.default_backend.def_backend`` (or pass ``backend=...`` to ``get_measurement``).  ``pm``: a Qrisp
+    ``PassManager`` applied to every circuit first, as ``QrispSimulatorBackend(pm=...)`` does
+    (qrisp_simulator_backend.py:262-330).  Needs Qrisp importable in the calling process; nothing else in this
+    package does."""
+    from qrisp.circuit.pass_management import PassManager
     from qrisp.interface.backend import Backend
     from qrisp.interface.job import Job, JobResult, JobStatus
 
@@ -197,19 +216,27 @@ def make_qrisp_backend(dtype=np.complex64, **engine_kwargs):
             return self._last_known_status
 
     class B200QrispBackend(Backend):
-        def __init__(self):
+        def __init__(self, pm=None):
             super().__init__(name="B200Simulator", options=None)
+            if pm is not None and not isinstance(pm, PassManager):
+                raise TypeError(f"Expected a PassManager instance for 'pm', got {type(pm).__name__}.")
+            self._pm = pm
 
         @classmethod
         def _default_options(cls):
             return {"shots": None, "token": ""}
 
         def run_async(self, circuits, shots=None):
+            self._check_circuit_limit(circuits)
             batch = list(circuits) if _is_batch(circuits) else [circuits]
+            if self._pm is not None:
+                batch = [self._pm.run(c) for c in batch]
+            if isinstance(shots, list):
+                self._validate_shots_length(shots, batch)
             if shots is None:
                 shots = self.options.get("shots")
             job = B200QrispJob(self, batch, shots)
             job.submit()
             return job
 
-    return B200QrispBackend()
+    return B200QrispBackend(pm)
