@@ -25,7 +25,7 @@ from __future__ import annotations
 
 import cmath
 import math
-from typing import Iterable, Sequence
+from typing import Sequence
 
 import numpy as np
 

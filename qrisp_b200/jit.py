@@ -30,7 +30,7 @@ import tempfile
 import threading
 
 from . import _lib
-from .planner import CHAIN_SHAPES, CODE_CHAIN, CODE_CXL, CODE_DBITS, CXL_SHAPES, FEATURE_FULL, FEATURE_TMA
+from .planner import CHAIN_SHAPES, CODE_CHAIN, CODE_CXL, CODE_DBITS, CXL_SHAPES, FEATURE_FULL
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")

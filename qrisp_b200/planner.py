@@ -28,8 +28,6 @@ import struct
 
 import numpy as np
 
-from .normalize import CMat, DiagTerm, Relabel
-
 QB2_PASS_MAGIC = 0x32425151
 QB2_C64, QB2_C128 = 0, 1
 OP_MAT = {1: 1, 2: 2, 3: 3, 4: 4}

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .circuit import NON_UNITARY, STRUCTURAL, Instruction, _controlled
+from .circuit import STRUCTURAL, Instruction, _controlled
 
 _CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
 

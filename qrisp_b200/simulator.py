@@ -68,8 +68,6 @@ def _device_outcomes(sv, mes_qubits):
     """Outcomes the reference keeps for more than 10 measured qubits, pruned ON THE DEVICE: the dense
     distribution (2**m doubles) stays in HBM, only ``p > max(p) * cutoff_ratio`` travels
     (reference: bi_arrays.py:1030-1055 -> bi_array_helper.py:315-331)."""
-    import ctypes
-
     import torch
 
     from . import _lib

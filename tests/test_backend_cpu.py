@@ -2,7 +2,6 @@
 options, the ``pm`` keyword, argument validation and the failure path -- everything in front of the first launch.
 The Qrisp form is checked against the unmodified reference package (oracle/_ref) when it is built."""
 
-import numpy as np
 import pytest
 
 from qrisp_b200.backend import B200Backend, B200JobResult, make_qrisp_backend

@@ -9,8 +9,8 @@ import pytest
 
 from oracle import pass_emulator, ref_sim
 from qrisp_b200 import preprocess, simulator
-from qrisp_b200.circuit import Circuit, ghz_qft_circuit, qft_circuit, random_circuit
-from qrisp_b200.normalize import CMat, DiagTerm, Relabel, normalize_circuit, normalize_instruction
+from qrisp_b200.circuit import Circuit, ghz_qft_circuit, random_circuit
+from qrisp_b200.normalize import normalize_circuit, normalize_instruction
 
 from helpers import canonical, emulate_statevector, marginal, plan_circuit
 

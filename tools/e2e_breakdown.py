@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from qrisp_b200.circuit import ghz_qft_circuit
-from qrisp_b200 import simulator, engine, prefix
+from qrisp_b200 import simulator, engine
 from qrisp_b200.normalize import normalize_circuit
 from qrisp_b200.planner import Planner
 from qrisp_b200.preprocess import unitarize
