@@ -20,6 +20,9 @@ Fixtures written (all small .npz files):
                       h + inverse QFT; configs[2]: Shor ``find_order``) + what ``run`` returned
 * fusion.npz       -- ``group_qc`` output: every grouped instruction's qubits and unitary
 * cif.npz          -- circuits with classically controlled operations (``op.c_if``) + ``run(qc, None)``
+* algorithms.npz   -- what callers of the path send: Qrisp programs (Grover, phase estimation, arithmetic,
+                      comparisons, logic synthesis, multi-controlled X by five methods, Dicke states, a QAOA layer pair, modular multiplication, division, uncomputation,
+                      amplitude amplification) captured at the backend boundary + what ``run`` returned
 * shor.npz         -- BASELINE.json configs[2] at the named sizes: ``find_order`` circuits for N=35 and
                       N=77 as Qrisp compiled them + what ``run`` returned + the reference's wall time
 """
@@ -394,6 +397,195 @@ def make_cif():
     print("cif.npz:", names)
 
 
+def make_algorithms():
+    """Programs from Qrisp's own repertoire, compiled by Qrisp, captured at the backend boundary: the callers of
+    the path.  Every case is what ``get_measurement`` / ``multi_measurement`` handed to the simulator."""
+    import networkx as nx
+    import qrisp.interface.simulators.qrisp_simulator_backend as be
+    from qrisp import (QPE, QuantumArray, QuantumBool, QuantumDictionary, QuantumModulus, QuantumString, QuantumVariable,
+                       amplitude_amplification, auto_uncompute, conjugate, control, cp, cx, dicke_state, mcx,
+                       multi_measurement, p, q_div, ry, x, z)
+    from qrisp.grover import grovers_alg, tag_state
+    from qrisp.qaoa import RX_mixer, create_maxcut_cost_operator
+
+    captured = []
+    orig = be.default_run
+
+    def spy(qc, shots, token=""):
+        res = orig(qc.copy(), shots, token)
+        captured.append((qc.copy(), res))
+        return res
+
+    be.default_run = spy
+    out, names = {}, []
+
+    def case(name, build):
+        n0 = len(captured)
+        quiet(build)
+        assert len(captured) == n0 + 1, name
+        qc, res = captured[-1]
+        pack(name + "_", Circuit.from_qrisp(qc), out)
+        keys = sorted(res.keys())
+        out[name + "_keys"] = np.array(keys)
+        out[name + "_probs"] = np.array([res[k] for k in keys], dtype=np.float64)
+        names.append(name)
+
+    def grover():
+        qf = QuantumFloat(4)
+        grovers_alg(qf, lambda v: tag_state({v: 5}))
+        qf.get_measurement()
+
+    def grover_two():
+        a, b = QuantumFloat(2), QuantumFloat(2)
+        grovers_alg([a, b], lambda vs: tag_state({vs[0]: 1, vs[1]: 2}))
+        multi_measurement([a, b])
+
+    def phase_estimation():
+        def u(qv):
+            p(2 * np.pi * 0.3125, qv[0])
+            p(2 * np.pi * 0.125, qv[1])
+
+        qv = QuantumVariable(2)
+        x(qv)
+        QPE(qv, u, precision=4).get_measurement()
+
+    def add_compare():
+        a, b = QuantumFloat(3), QuantumFloat(3)
+        h(a[0]), h(a[2])
+        b[:] = 3
+        c = a + b
+        multi_measurement([a, c, c < 6])
+
+    def sub_signed():
+        a, b = QuantumFloat(3, signed=True), QuantumFloat(3, -1)
+        a[:] = -2
+        h(b[0]), h(b[1])
+        multi_measurement([b, a - b])
+
+    def inplace_add():
+        a, b = QuantumFloat(4), QuantumFloat(4)
+        h(a[:2])
+        b[:] = 5
+        b += a
+        multi_measurement([a, b])
+
+    def logic():
+        a, b, c = QuantumBool(), QuantumBool(), QuantumBool()
+        h(a), h(b), h(c)
+        multi_measurement([a, b, c, (a & b) | c])
+
+    def mcx_by(method, controls=5):
+        def build():
+            qv, t = QuantumVariable(controls), QuantumBool()
+            for i in range(controls):
+                (x if i in (2, 3) and controls > 2 else h)(qv[i])
+            mcx(list(qv), t[0], method=method)
+            multi_measurement([qv, t])
+
+        return build
+
+    def dictionary():
+        qd = QuantumDictionary(return_type=QuantumFloat(3))
+        for i in range(8):
+            qd[i] = (i * i) % 8
+        k = QuantumFloat(3)
+        h(k)
+        multi_measurement([k, qd[k]])
+
+    def array():
+        qa = QuantumArray(qtype=QuantumFloat(2), shape=(3,))
+        qa[:] = [1, 2, 3]
+        h(qa[0][0])
+        multi_measurement([qa[0], qa[0] + qa[1]])
+
+    def dicke():
+        qv = QuantumVariable(5)
+        x(qv[3]), x(qv[4])
+        dicke_state(qv, 2)
+        qv.get_measurement()
+
+    def string():
+        s = QuantumString(size=2)
+        s[:] = "ab"
+        h(s[0][0])
+        s.get_measurement()
+
+    def qaoa_layers():
+        g = nx.cycle_graph(6)
+        g.add_edge(0, 3)
+        qarg = QuantumVariable(6)
+        h(qarg)
+        cost = create_maxcut_cost_operator(g)
+        for gamma, beta in ((0.4, 0.7), (0.9, 0.3)):
+            cost(qarg, gamma)
+            RX_mixer(qarg, beta)
+        qarg.get_measurement()
+
+    def modular_mul():
+        a, b = QuantumModulus(13), QuantumModulus(13)
+        a[:] = 5
+        h(b[0]), h(b[1])
+        multi_measurement([b, a * b])
+
+    def division():
+        a, b = QuantumFloat(3), QuantumFloat(3)
+        a[:] = 6
+        b[:] = 2
+        h(a[0])
+        multi_measurement([a, q_div(a, b, prec=1)])
+
+    def uncompute():
+        @auto_uncompute
+        def f(a, b):
+            r = QuantumBool()
+            cx((a * b)[0], r)
+            return r
+
+        a, b = QuantumFloat(2), QuantumFloat(2)
+        h(a), h(b)
+        multi_measurement([a, b, f(a, b)])
+
+    def amplification():
+        def state(qb):
+            ry(0.5, qb[0])
+
+        qb = QuantumBool()
+        state(qb)
+        amplitude_amplification([qb], state, lambda q: z(q[0]), iter=2)
+        qb.get_measurement()
+
+    def conjugation():
+        qv = QuantumFloat(4)
+        h(qv)
+        with conjugate(QFT)(qv):
+            p(0.3, qv[1])
+            cp(0.2, qv[0], qv[2])
+        with control(qv[3]):
+            x(qv[0])
+        qv.get_measurement()
+
+    for name, build in (
+        ("grover_float4", grover), ("grover_two_floats", grover_two), ("phase_estimation", phase_estimation),
+        ("add_compare", add_compare), ("sub_signed_exponent", sub_signed), ("inplace_add", inplace_add), ("logic", logic),
+        ("mcx_gray", mcx_by("gray")), ("mcx_gray_pt", mcx_by("gray_pt")), ("mcx_balauca", mcx_by("balauca")),
+        ("mcx_yong", mcx_by("yong")), ("mcx_jones", mcx_by("jones", 2)),
+        ("quantum_dictionary", dictionary), ("quantum_array", array), ("dicke_state", dicke), ("quantum_string", string),
+        ("qaoa_maxcut_two_layers", qaoa_layers), ("modular_mul", modular_mul), ("division", division),
+        ("auto_uncompute", uncompute), ("amplitude_amplification", amplification), ("conjugation_control", conjugation),
+    ):
+        try:
+            case(name, build)
+        except Exception as e:  # pragma: no cover - depends on the stubbed imports
+            print("algorithms:", name, "failed under stubs:", repr(e)[:200])
+    be.default_run = orig
+    out["cases"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "algorithms.npz"), **out)
+    print("algorithms.npz:", names)
+
+
+# ------------------------------------------------------------------------------------
+
+
 def make_shor(only=None):
     """BASELINE.json configs[2] at the sizes it names (README ``find_order``, N = 35 and N = 77), captured at
     the backend boundary like make_programs; the reference's own wall time goes along.  Every case is saved as
@@ -481,5 +673,6 @@ if __name__ == "__main__":
     make_run()
     make_programs()
     make_cif()
+    make_algorithms()
     make_shor()
     make_fusion()

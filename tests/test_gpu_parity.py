@@ -688,3 +688,25 @@ def test_specialised_pass_kernels_match_the_interpreter(sim):
         prog.run()
         np.testing.assert_allclose(sv.statevector(), ref_sim.statevector(qc), atol=ATOL64)
     assert keys[0] == keys[1]
+
+
+# ---------------------------------------------------------------------------------------
+# the callers of the path: programs from Qrisp's own repertoire (kept last in this file)
+# ---------------------------------------------------------------------------------------
+
+
+def test_qrisp_algorithms_match_reference_results(golden_dir, sim):
+    """Grover, phase estimation, arithmetic and comparisons, logic synthesis, multi-controlled X by five
+    methods, Dicke states, QAOA layers, modular multiplication, division, uncomputation, amplitude
+    amplification -- compiled by Qrisp, captured at the backend boundary together with what the reference's
+    ``run`` returned (tests/golden/make_golden.py: make_algorithms): same labels, probabilities within 1e-5."""
+    g = load(golden_dir, "algorithms.npz")
+    assert len(g["cases"]) >= 20
+    for case in g["cases"]:
+        case = str(case)
+        qc = Circuit.from_arrays(g, case + "_")
+        got = sim.run(qc, None)
+        ref = {str(k): float(p) for k, p in zip(g[case + "_keys"], g[case + "_probs"])}
+        assert set(got) == set(ref), case  # basis-state labels bit-exact
+        for k in ref:
+            assert abs(got[k] - ref[k]) < ATOL64, (case, k)

@@ -79,7 +79,7 @@ def _assert_dist_close(got, ref, atol=1e-5):
         assert abs(got.get(k, 0.0) - ref.get(k, 0.0)) <= atol, (k, got.get(k), ref.get(k))
 
 
-@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz", "cif.npz"])
+@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz", "cif.npz", "algorithms.npz"])
 def test_oracle_run_matches_reference(golden_dir, fixture):
     g = load(golden_dir, fixture)
     for case in g["cases"]:

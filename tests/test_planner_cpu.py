@@ -298,7 +298,7 @@ def _run_emulated(qc):
     return res
 
 
-@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz", "cif.npz"])
+@pytest.mark.parametrize("fixture", ["run.npz", "programs.npz", "cif.npz", "algorithms.npz"])
 def test_run_matches_reference_results(golden_dir, fixture):
     g = load(golden_dir, fixture)
     for case in g["cases"]:
@@ -312,7 +312,7 @@ def test_run_matches_reference_results(golden_dir, fixture):
             assert abs(got.get(k, 0.0) - ref.get(k, 0.0)) < 1e-5, (case, k)
 
 
-@pytest.mark.parametrize("fixture", ["run.npz", "cif.npz"])
+@pytest.mark.parametrize("fixture", ["run.npz", "cif.npz", "algorithms.npz"])
 def test_unitarize_matches_oracle_rewriting(golden_dir, fixture):
     g = load(golden_dir, fixture)
     for case in g["cases"]:
