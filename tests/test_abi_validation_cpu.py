@@ -138,3 +138,77 @@ def test_lean_pass_with_a_two_qubit_matrix_is_refused():
     struct.pack_into("<I", lean, 56, features & ~FEATURE_FULL)
     rc, msg = _call(lean, n)
     assert rc == EINVAL and "full kernel" in msg
+
+
+def test_argument_checks_of_the_other_entry_points():
+    """Bad arguments come back as QB2_EINVAL / QB2_ELIMIT with a message that names the function, before any
+    device work (the reference raises Python exceptions at the same places: wrong qubit lists, shapes)."""
+    lib = _lib.load()
+
+    def ints(*v):
+        return (ctypes.c_int * len(v))(*v)
+
+    def refused(rc, who, code=EINVAL):
+        msg = lib.qb2_last_error().decode(errors="replace")
+        assert rc == code, (who, rc, msg)
+        assert who in msg, (who, msg)
+
+    other = ctypes.c_void_p(2 << 20)
+    n = 20
+    # layout
+    refused(lib.qb2_permute_bits(FAKE, other, 4, ints(0, 1, 1, 3), 0, None), "qb2_permute_bits")  # not a permutation
+    refused(lib.qb2_permute_bits(FAKE, FAKE, 4, ints(0, 1, 2, 3), 0, None), "qb2_permute_bits")  # in place
+    peers = (ctypes.c_void_p * 2)(1 << 20, 2 << 20)
+    refused(lib.qb2_swap_pull(other, peers, 3, 0, n, None, 0, None), "qb2_swap_pull")  # not a power of two
+    refused(lib.qb2_swap_pull(other, peers, 2, 2, n, None, 0, None), "qb2_swap_pull")  # rank outside the world
+    refused(lib.qb2_swap_pull(other, peers, 2, 0, 4, ints(1, 0, 2, 3), 0, None), "qb2_swap_pull")  # complex64 moves position 0
+    refused(lib.qb2_swap_pull(other, peers, 2, 0, 4, ints(0, 2, 2, 3), 0, None), "qb2_swap_pull")
+    peers[1] = None
+    refused(lib.qb2_swap_pull(other, peers, 2, 0, 4, None, 0, None), "qb2_swap_pull")  # null peer
+    # measurement
+    refused(lib.qb2_probabilities(FAKE, n, 0, ints(3, 3), 2, other, 0, None), "qb2_probabilities")  # duplicate position
+    refused(lib.qb2_probabilities(None, n, 0, ints(3), 1, other, 0, None), "qb2_probabilities")
+    refused(lib.qb2_norm2(FAKE, 41, other, 0, None), "qb2_norm2")
+    refused(lib.qb2_sample_scan(None, 16, None), "qb2_sample_scan")
+    refused(lib.qb2_prune_probabilities(FAKE, 12, 2e-4, other, None, None, 8, None), "qb2_prune_probabilities")  # capacity without outputs
+    # dense blocks
+    refused(lib.qb2_apply_matrix_big(FAKE, other, n, 0, FAKE, ints(*range(11)), 11, 0, 0, 0, None), "qb2_apply_matrix_big", ELIMIT)
+    refused(lib.qb2_apply_matrix_big(FAKE, other, n, 0, FAKE, ints(1, 1, 2), 3, 0, 0, 0, None), "qb2_apply_matrix_big")
+    refused(lib.qb2_apply_matrix_big(FAKE, other, n, 0, FAKE, ints(1, 2, 3), 3, 1 << 2, 1 << 2, 0, None), "qb2_apply_matrix_big")  # control on a target
+    refused(lib.qb2_apply_block_tc(FAKE, n, 0, other, ints(0, 1, 2, 4, 3), 0, 0, None), "qb2_apply_block_tc")  # not ascending
+    refused(lib.qb2_apply_block_tc(FAKE, n, 0, other, ints(0, 1, 2, 3, 4), 1 << 3, 1 << 3, None), "qb2_apply_block_tc")  # control on a target
+    refused(lib.qb2_apply_block_tc(FAKE, 8, 0, other, ints(0, 1, 2, 3, 4), 0, 0, None), "qb2_apply_block_tc")  # too narrow
+    refused(lib.qb2_apply_block_tc(None, n, 0, other, ints(0, 1, 2, 3, 4), 0, 0, None), "qb2_apply_block_tc")
+    refused(lib.qb2_apply_mux_ry(FAKE, n, 0, 3, ints(3), 1, other, 0, 0, 0, None), "qb2_apply_mux_ry")  # control = target
+    refused(lib.qb2_apply_mux_ry(FAKE, n, 0, 3, ints(*range(4, 12)), 8, other, 0, 0, 0, None), "qb2_apply_mux_ry")  # too many controls
+    refused(lib.qb2_pack_block_tc(None, None), "qb2_pack_block_tc")
+    # specialised kernels
+    refused(lib.qb2_jit_load(None, None), "qb2_jit_load")
+    refused(lib.qb2_run_pass_jit(None, FAKE, n, 0, FAKE, FAKE, 0, None, None, 0), "qb2_run_pass_jit")
+    # host prefix
+    count, consumed = ctypes.c_uint32(5), ctypes.c_int32(0)
+    refused(lib.qb2_sparse_prefix(0, None, None, None, None, 4, 1e-14, other, other, ctypes.byref(count), ctypes.byref(consumed)),
+            "qb2_sparse_prefix")  # list longer than its capacity
+
+
+def test_pack_block_tc_splits_into_two_tf32_halves():
+    """Host half of the tensor-core block (qb2_pack_block_tc): the 32 x 32 complex matrix as the real 64 x 64
+    operand with re / im interleaved per row and column ([[re, -im], [im, re]] per entry), each value as a TF32
+    high part plus a TF32 low part, both in the canonical K-major no-swizzle UMMA layout (8-row x 16-byte core
+    matrices, 128 B between K chunks, 2 KB between row groups).  hi + lo gives the value back to 2**-21."""
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    a = rng.normal(size=(32, 32)) + 1j * rng.normal(size=(32, 32))
+    u = np.ascontiguousarray(np.linalg.qr(a)[0].astype(np.complex128))
+    out = np.zeros(_lib.QB2_BLOCK_TC_BYTES // 4, dtype=np.float32)
+    assert lib.qb2_pack_block_tc(u.ctypes.data, out.ctypes.data) == 0
+    assert not np.any(out.view(np.uint32) & np.uint32(0x1FFF)), "every stored word is a TF32 value (13 low mantissa bits clear)"
+    hi, lo = out[: out.size // 2].astype(np.float64), out[out.size // 2 :].astype(np.float64)
+    row, k = np.meshgrid(np.arange(64), np.arange(64), indexing="ij")
+    off = ((row >> 3) * 2048 + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4) // 4
+    assert sorted(off.ravel().tolist()) == list(range(64 * 64))  # the layout is a permutation of the tile
+    entry = u[row >> 1, k >> 1]
+    want = np.where(row & 1, np.where(k & 1, entry.real, entry.imag), np.where(k & 1, -entry.imag, entry.real))
+    got = hi[off] + lo[off]
+    assert np.abs(got - want).max() < 2.0**-21
+    assert np.abs(hi[off] - want).max() < 2.0**-10 and np.abs(hi[off] - want).max() > 0  # hi alone is only TF32
