@@ -144,6 +144,21 @@ def rxx_matrix(phi):
     return np.array([[c, 0, 0, s], [0, c, s, 0], [0, s, c, 0], [s, 0, 0, c]], dtype=np.complex128)
 
 
+def r_matrix(theta, phi):
+    """Rotation by ``theta`` about the axis cos(phi) X + sin(phi) Y in the reference's convention
+    (standard_operations.py RGate; pinned by tests/golden/gates.npz)."""
+    c, s = math.cos(theta / 2), math.sin(theta / 2)
+    return np.array([[c, cmath.exp(-1j * phi) * s], [-cmath.exp(1j * phi) * s, c]], dtype=np.complex128)
+
+
+def xxyy_matrix(phi, beta):
+    """exp(-i phi/4 (XX + YY)) with the phase ``beta`` on the exchanged pair (standard_operations.py XXYYGate;
+    pinned by tests/golden/gates.npz): |01> and |10> rotate into each other, |00> and |11> stay."""
+    c, s = math.cos(phi / 2), -1j * math.sin(phi / 2)
+    return np.array([[1, 0, 0, 0], [0, c, s * cmath.exp(1j * beta), 0], [0, s * cmath.exp(-1j * beta), c, 0], [0, 0, 0, 1]],
+                    dtype=np.complex128)
+
+
 class Circuit:
     """A flat list of :class:`Instruction` over ``num_qubits`` qubits and ``num_clbits`` clbits."""
 
@@ -229,6 +244,15 @@ class Circuit:
     def sx(self, q):
         return self.append("sx", q, matrix=GATE_SX)
 
+    def sx_dg(self, q):
+        return self.append("sx_dg", q, matrix=GATE_SX.conj().T)
+
+    def id(self, q):
+        return self.append("id", q, matrix=np.eye(2, dtype=np.complex128))
+
+    def r(self, theta, phi, q):
+        return self.append("r", q, matrix=r_matrix(theta, phi), params=(theta, phi))
+
     def p(self, phi, q):
         return self.append("p", q, matrix=p_matrix(phi), params=(phi,))
 
@@ -261,6 +285,12 @@ class Circuit:
 
     def crz(self, phi, c, t):
         return self.append("crz", (c, t), matrix=_controlled(rz_matrix(phi)), params=(phi,))
+
+    def crx(self, phi, c, t):
+        return self.append("crx", (c, t), matrix=_controlled(rx_matrix(phi)), params=(phi,))
+
+    def xxyy(self, phi, beta, a, b):
+        return self.append("xxyy", (a, b), matrix=xxyy_matrix(phi, beta), params=(phi, beta))
 
     def swap(self, a, b):
         return self.append("swap", (a, b), matrix=GATE_SWAP)

@@ -91,6 +91,11 @@ def make_gates():
         ("swap", lambda qc: qc.swap(0, 1), 2),
         ("rzz", lambda qc: qc.rzz(0.37, 0, 1), 2),
         ("rxx", lambda qc: qc.rxx(0.37, 0, 1), 2),
+        ("sx_dg", lambda qc: qc.sx_dg(0), 1),
+        ("id", lambda qc: qc.id(0), 1),
+        ("r", lambda qc: qc.r(0.37, 1.1, 0), 1),
+        ("crx", lambda qc: qc.crx(0.37, 0, 1), 2),
+        ("xxyy", lambda qc: qc.xxyy(0.37, 1.1, 0, 1), 2),
         ("mcx", lambda qc: qc.mcx([0, 1], 2), 3),
         ("mcp", lambda qc: qc.append(PGate(0.37).control(2), [qc.qubits[0], qc.qubits[1], qc.qubits[2]]), 3),
     ]

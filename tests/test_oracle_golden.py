@@ -28,6 +28,8 @@ def test_gate_library_matches_reference_unitaries(golden_dir):
         "swap": lambda qc: qc.swap(0, 1), "rzz": lambda qc: qc.rzz(0.37, 0, 1),
         "rxx": lambda qc: qc.rxx(0.37, 0, 1), "mcx": lambda qc: qc.mcx([0, 1], 2),
         "mcp": lambda qc: qc.mcp(0.37, [0, 1], 2),
+        "sx_dg": lambda qc: qc.sx_dg(0), "id": lambda qc: qc.id(0), "r": lambda qc: qc.r(0.37, 1.1, 0),
+        "crx": lambda qc: qc.crx(0.37, 0, 1), "xxyy": lambda qc: qc.xxyy(0.37, 1.1, 0, 1),
     }
     assert set(build) == set(str(n) for n in g["names"])
     for name in g["names"]:
