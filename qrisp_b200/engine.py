@@ -398,8 +398,8 @@ class StateVector(DeviceOps):
     def compile(self, instructions):
         """Normalise + plan a list of unitary instructions against the CURRENT qubit map (and, when the
         state is still pending, the current sparse state: the program then starts with the host
-        prefix).  Returns a compiled program that :meth:`execute` runs; map and state move on as if the
-        program had run."""
+        prefix).  Returns a compiled program that :meth:`execute` runs; map and state stay what they were
+        (running the program moves them)."""
         pos_in = list(self.pos)
         start = self._pending
         instructions = self._take_prefix(list(instructions))
@@ -451,11 +451,13 @@ class StateVector(DeviceOps):
                 self._run_big(step)
                 self.stats["gate_ops"] += 1
 
-        steps, need = planner.plan(ops, on_step=launch)
+        try:
+            steps, need = planner.plan(ops, on_step=launch)
+        finally:
+            self._entry_pos = None
         if need is not None:
             raise _lib.Qb2Error(f"op needs non-local positions {need} on a single-device state")
         self._keep_alive = keep
-        self._entry_pos = None
         return steps
 
     def apply_matrix(self, matrix, qubits):
