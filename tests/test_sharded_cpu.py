@@ -125,7 +125,7 @@ def _worker(rank, world, port, case, out_dir):
         elif case == "soup":
             from soup import gate_soup
 
-            qc = gate_soup(13, 120, np.random.default_rng(99), wide=True)
+            qc = gate_soup(13, 120, np.random.default_rng(int(os.environ.get("QB2_FUZZ_SEED", 99))), wide=True)
         elif case == "random":
             qc = random_circuit(13, 6, seed=21, two_qubit="cx")
             qc.mcx([0, 12], 6)
