@@ -1,4 +1,4 @@
-"""The multi-GPU path on CPU: world_size 2 and 4 over gloo.
+"""The multi-GPU path on CPU: world_size 2, 4 and 8 over gloo.
 
 The sharding logic (swap planning, position bookkeeping, the all-to-all exchange, rank bits
 in ``hi_base``) is the product code of ``qrisp_b200/distributed.py``; only the four device
@@ -143,6 +143,7 @@ def _worker(rank, world, port, case, out_dir):
         sv = CpuShard(13)
         prog = sv.compile(instrs)
         prog.run()
+        sv._materialize()  # (a circuit the host prefix absorbs whole leaves the state pending)
         shards = [torch.empty_like(sv.state) for _ in range(world)]
         dist.all_gather(shards, sv.state)
         full = torch.cat(shards).numpy().view(np.complex64)
@@ -153,6 +154,7 @@ def _worker(rank, world, port, case, out_dir):
         # the streaming path (apply_circuit: every step launched the moment it is planned) gives the same state
         sv2 = CpuShard(13)
         steps2 = sv2.apply_circuit(instrs)
+        sv2._materialize()
         shards = [torch.empty_like(sv2.state) for _ in range(world)]
         dist.all_gather(shards, sv2.state)
         got2 = _canonical(torch.cat(shards).numpy().view(np.complex64), sv2.pos, 13)
@@ -166,7 +168,7 @@ def _worker(rank, world, port, case, out_dir):
 
 
 @pytest.mark.parametrize("world,case", [(2, "qft"), (2, "random"), (4, "qft"), (4, "random"), (2, "big"), (4, "soup"), (2, "soup"), (2, "qft_fixed_layout"),
-                                        (4, "qft_long_prefix"), (2, "soup_long_prefix")])
+                                        (4, "qft_long_prefix"), (2, "soup_long_prefix"), (8, "qft_long_prefix"), (8, "random")])
 def test_sharded_statevector_over_gloo(tmp_path, world, case):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, case, str(tmp_path)), nprocs=world, join=True)
